@@ -1,0 +1,502 @@
+#!/usr/bin/env python
+"""bench.py -- splat forward+backward throughput of the surfel rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward + one backward of the rasterizer over one camera of the synthetic workload
+(default C3: 1 M surfels, 1920x1080, SH degree 3).  Rank 0 prints ONE JSON line.
+
+  value      Msurfel*pixels/s = 256 * I / t_step / 1e6 (I = instances of the step's camera), inputs resident in
+             HBM, persistent workspaces, no host round trip inside the timed region (eggfusion_b200.pipeline)
+  e2e        the same metric through the reference-facing public API (GaussianRasterizer + loss.backward()),
+             with the step's camera matrices and target RGB-D frame copied from pinned host memory and the loss
+             read back to the host inside the timed region
+  roofline   dominant kernel: algorithmic bytes (SURVEY 8d formula) / its CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (oracle/splat_oracle.c, OpenMP) on a bounded sample of the same workload
+  --impl reference   the unmodified reference rasterizer (oracle/_ref, compiled for sm_100a from /root/reference)
+             through its own public API on the same GPU, same scene, same loop; if that build is absent the CPU
+             oracle port is timed instead.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "splat_fwd_bwd_surfel_pixels_per_s"
+UNIT = "Msurfel*pixels/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML, ~20 ms period)."""
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_workload(name):
+    """Scene + 4 cameras (small pose changes) + per-camera pixel gradients / target frames, all numpy."""
+    from eggfusion_b200 import synthetic as syn
+    P, W, H, L, deg = syn.CONFIGS[name]
+    base = syn.default_camera(W, H)
+    scene = syn.make_scene(P, base, layers=L, sh_degree=deg)
+    poses = [None, ((0.04, -0.02, 0.03), 0.02, -0.015), ((-0.03, 0.03, -0.02), -0.025, 0.01),
+             ((0.02, 0.04, 0.05), 0.015, 0.02)]
+    cams = [base if p is None else syn.default_camera(W, H, syn.look_from(*p)) for p in poses]
+    grads = [syn.make_pixel_grads(c, seed=syn.SEED + 1 + i) for i, c in enumerate(cams)]
+    return scene, cams, grads, deg
+
+
+def algorithmic_bytes(P, P_vis, I, N_px, M):
+    """bytes each stage must move at least once."""
+    b = {
+        "surfel_forward": P * (49 + 12 * M) + 64 * P_vis,
+        "emit_sort": 28 * I,
+        "render_forward": 68 * I + 44 * N_px,
+        "render_backward": 44 * N_px + 68 * I + 60 * P_vis,
+        "surfel_backward": 124 * P_vis + P * (88 + 24 * M),
+    }
+    b["A_fwd"] = b["surfel_forward"] + b["emit_sort"] + b["render_forward"]
+    b["A_bwd"] = b["render_backward"] + b["surfel_backward"]
+    return b
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline_sample(scene, cam, grad, deg, rows_mod=2):
+    """Oracle port (C, OpenMP) on a bounded sample: every `rows_mod`-th tile row of the workload's first camera."""
+    from oracle import oracle as orc
+    M = scene["shs"].shape[1]
+    oc = orc.cam_from_synthetic(cam, deg, M)
+    ty, tx = cam.tiles
+    mask = np.zeros((ty, tx), np.int32)
+    mask[::rows_mod, :] = 1
+    t0 = time.perf_counter()
+    f = orc.forward(oc, scene["xyz"], scene["scales"], scene["rotations"], scene["opacity"], scene["shs"],
+                    tile_mask=mask)
+    orc.backward(oc, f, scene["xyz"], scene["scales"], scene["rotations"], scene["shs"], grad["color"],
+                 grad["normal"], grad["depth"], grad["opacity"])
+    dt = time.perf_counter() - t0
+    I = f["num_rendered"]
+    return {"value": 256.0 * I / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": "1 fwd+bwd of camera 0, every %d-th tile row (%d of %d tile rows, %d instances), %.1f s"
+                      % (rows_mod, len(range(0, ty, rows_mod)), ty, I, dt)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import eggfusion_b200 as E
+    from eggfusion_b200 import parallel as par
+    from eggfusion_b200 import rasterizer as R
+    from eggfusion_b200.pipeline import SplatContext
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E.load()
+    scene, cams, grads, deg = make_workload(args.workload)
+    P, M = scene["xyz"].shape[0], scene["shs"].shape[1]
+    W, H = cams[0].width, cams[0].height
+    N_px = W * H
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    params = {k: t(scene[k]) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
+    bg = t(np.zeros(3, np.float32))
+    settings = [E.GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
+        viewmatrix=t(c.viewmatrix), projmatrix=t(c.projmatrix), sh_degree=deg, campos=t(c.campos), prefiltered=False,
+        debug=False, cx=c.cx, cy=c.cy) for c in cams]
+    pix = [tuple(t(g[k]) for k in ("color", "normal", "depth", "opacity")) for g in grads]
+    ty, tx = cams[0].tiles
+    mask = par.tile_partition(ty, tx, world, rank).to(dev) if world > 1 else None
+    empty = torch.Tensor([])
+
+    # instance counts per camera (exact mode, outside the timed region) -> capacity of the persistent context
+    I_cam, vis_cam = [], []
+    for s in settings:
+        out = R.forward_raw(s, params["xyz"], params["shs"], empty, params["opacity"], params["scales"],
+                            params["rotations"], mask)
+        I_cam.append(out[6].num_rendered)
+        vis_cam.append(int((out[5] > 0).sum()))
+        del out
+    cap = int(max(I_cam) * 1.05) + 4096
+    Pp = par.padded_rows(P, world)
+    ctx = SplatContext(P, W, H, M, cap, device=dev, padded_rows=Pp)
+    first, count = par.surfel_range(P, world, rank)
+    chunk = Pp // world
+
+    stage_ev = {}
+
+    def one_step(i, timed):
+        ci = i % len(settings)
+        ctx.set_camera(settings[ci])
+        marks = []
+
+        def mark(name):
+            if timed:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        if timed:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            marks.append(("start", e0))
+        ctx.forward(params["xyz"], params["shs"], None, params["opacity"], params["scales"], params["rotations"],
+                    mask, mark)
+        ctx.backward_render(*pix[ci], mark=mark)
+        if world > 1:
+            mine = par.reduce_scatter_rows(ctx.screen, None)
+            mark("reduce_scatter")
+            base = mine.data_ptr() - rank * chunk * 64
+            ctx.backward_surfels(params["xyz"], params["shs"], None, params["scales"], params["rotations"], first,
+                                 count, screen_base=base, mark=mark)
+        else:
+            ctx.backward_surfels(params["xyz"], params["shs"], None, params["scales"], params["rotations"],
+                                 mark=mark)
+        if timed:
+            stage_ev[i] = marks
+        return ci
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        one_step(i, False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    used = [one_step(i, True) for i in range(args.steps)]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    counters = ctx.read_counters()
+    assert counters[2] == 0, "binning capacity overflow inside the timed region"
+
+    # per-stage means over the timed steps
+    stage_ms = {}
+    for marks in stage_ev.values():
+        for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
+            stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+
+    I_mean = float(np.mean([I_cam[c] for c in used]))
+    vis_mean = float(np.mean([vis_cam[c] for c in used]))
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    Isum = torch.tensor([I_mean], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Isum, op=dist.ReduceOp.SUM)
+    ms_step = float(tmax.item()) / args.steps
+    I_total = float(Isum.item())
+    value = 256.0 * I_total / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e through the public API, host buffers in the timed region (rank-local tiles when sharded)
+    e2e = None
+    if not args.no_e2e:
+        tgt_host = [(torch.from_numpy(np.random.default_rng(7 + i).uniform(0, 1, (3, H, W)).astype(np.float32)).pin_memory(),
+                     torch.from_numpy(np.random.default_rng(70 + i).uniform(1, 3, (1, H, W)).astype(np.float32)).pin_memory())
+                    for i in range(len(cams))]
+        cam_host = [(torch.from_numpy(c.viewmatrix.copy()).pin_memory(), torch.from_numpy(c.projmatrix.copy()).pin_memory(),
+                     torch.from_numpy(c.campos.copy()).pin_memory()) for c in cams]
+        leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        h2d = 4 * (4 * H * W) + 4 * (16 + 16 + 3)
+        losses = []
+
+        def e2e_step(i):
+            ci = i % len(cams)
+            c = cams[ci]
+            view, proj, campos = (x.to(dev, non_blocking=True) for x in cam_host[ci])
+            tc, td = (x.to(dev, non_blocking=True) for x in tgt_host[ci])
+            s = E.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, view, proj, deg, campos, False,
+                                                False, c.cx, c.cy)
+            color, normal, depth, opac, _a, _r = E.GaussianRasterizer(s)(
+                means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
+                rotations=leaf["rotations"], tile_mask=mask)
+            loss = (color - tc).abs().mean() + (depth - td).abs().mean() + 0.1 * (1 - normal[2]).mean()
+            loss.backward()
+            for v in leaf.values():
+                v.grad = None
+            losses.append(loss.item())  # D2H of the step's result
+        for i in range(max(3, args.warmup)):
+            e2e_step(i)
+        barrier()
+        n_e2e = args.steps
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n_e2e):
+            e2e_step(i)
+        b.record()
+        barrier()
+        t_e2e = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t_e2e.item()) / n_e2e
+        e2e = {"value": 256.0 * I_total / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+               "frames_per_s": 1e3 / ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 16,
+               "api": "eggfusion_b200.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    ab = algorithmic_bytes(P, vis_mean, I_mean, N_px, M)
+    kern_of = {"plan": "surfel_forward", "render": None, "bwd_render": "render_backward",
+               "bwd_surfels": "surfel_backward"}
+    dom_stage = max((k for k in stage_ms if k in ("plan", "render", "bwd_render", "bwd_surfels")),
+                    key=lambda k: stage_ms[k])
+    if dom_stage == "render":
+        dom_kernel, dom_bytes = "k_render_forward(+k_emit,k_tile_sort)", ab["emit_sort"] + ab["render_forward"]
+    else:
+        dom_kernel, dom_bytes = "k_" + kern_of[dom_stage], ab[kern_of[dom_stage]]
+    achieved = dom_bytes / (stage_ms[dom_stage] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d surfels @%dx%d, SH degree %d, 4 cameras cycled, 'layers' scene seed %d"
+                               % (args.workload, P, W, H, deg, 20251201),
+                   "l2_policy": "inputs larger than L2 (params %.0f MB + records %.0f MB per step; 126 MB L2)"
+                                % (P * (44 + 12 * M) / 1e6, 64 * P / 1e6),
+                   "parallelism": "tiles%d" % world if world > 1 else "single",
+                   "instances_per_frame": I_total, "visible_surfels": vis_mean},
+        "frames_per_s": 1e3 / ms_step,
+        "nominal_surfel_pixels_per_s_M": P * N_px / (ms_step * 1e-3) / 1e6,
+        "stage_ms": stage_ms,
+        "hbm_frac_step": (ab["A_fwd"] + ab["A_bwd"]) / (ms_step * 1e-3) / 1e9 / peak,
+        "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": dom_bytes, "kernel_ms": stage_ms[dom_stage]},
+        "clocks": clocks,
+        "gpu_launches": 7 * args.steps,
+        "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_sample(scene, cams[0], grads[0], deg)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from oracle import ref_loader
+    scene, cams, grads, deg = make_workload(args.workload)
+    P, M = scene["xyz"].shape[0], scene["shs"].shape[1]
+    W, H = cams[0].width, cams[0].height
+    have_gpu_ref = False
+    try:
+        import torch
+        have_gpu_ref = ref_loader.available() and torch.cuda.is_available()
+    except Exception:
+        pass
+    if not have_gpu_ref:
+        # no compiled reference on this box: time the CPU port of its algorithm on a bounded sample
+        cb = cpu_baseline_sample(scene, cams[0], grads[0], deg)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+                          "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": args.workload}, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    ref = ref_loader.load()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    params = {k: t(scene[k]) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
+    bg = t(np.zeros(3, np.float32))
+    ty, tx = cams[0].tiles
+    mask = torch.ones((ty, tx), dtype=torch.int32, device=dev)
+    settings = [ref.GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
+        viewmatrix=t(c.viewmatrix), projmatrix=t(c.projmatrix), sh_degree=deg, campos=t(c.campos), prefiltered=False,
+        debug=False, cx=c.cx, cy=c.cy) for c in cams]
+    pix = [tuple(t(g[k]) for k in ("color", "normal", "depth", "opacity")) for g in grads]
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    I_cam = []
+
+    def dev_step(i):
+        ci = i % len(cams)
+        color, normal, depth, opac, _a, _r = ref.GaussianRasterizer(settings[ci])(
+            means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
+            rotations=leaf["rotations"], tile_mask=mask)
+        torch.autograd.backward([color, normal, depth, opac], list(pix[ci]))
+        for v in leaf.values():
+            v.grad = None
+        return ci
+
+    # instance counts via the reference's own return value
+    empty = torch.Tensor([])
+    for s in settings:
+        out = ref._C.rasterize_gaussians(s.bg, params["xyz"], empty, params["opacity"], params["scales"],
+                                         params["rotations"], 1.0, empty, s.viewmatrix, s.projmatrix, mask,
+                                         s.tanfovx, s.tanfovy, H, W, s.cx, s.cy, params["shs"], deg, s.campos, False,
+                                         False)
+        I_cam.append(int(out[0]))
+        del out
+    for i in range(args.warmup):
+        dev_step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    used = [dev_step(i) for i in range(args.steps)]
+    b.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_step = a.elapsed_time(b) / args.steps
+    I_mean = float(np.mean([I_cam[c] for c in used]))
+    value = 256.0 * I_mean / (ms_step * 1e-3) / 1e6
+
+    tgt_host = [(torch.from_numpy(np.random.default_rng(7 + i).uniform(0, 1, (3, H, W)).astype(np.float32)).pin_memory(),
+                 torch.from_numpy(np.random.default_rng(70 + i).uniform(1, 3, (1, H, W)).astype(np.float32)).pin_memory())
+                for i in range(len(cams))]
+    cam_host = [(torch.from_numpy(c.viewmatrix.copy()).pin_memory(), torch.from_numpy(c.projmatrix.copy()).pin_memory(),
+                 torch.from_numpy(c.campos.copy()).pin_memory()) for c in cams]
+    losses = []
+
+    def e2e_step(i):
+        ci = i % len(cams)
+        c = cams[ci]
+        view, proj, campos = (x.to(dev, non_blocking=True) for x in cam_host[ci])
+        tc, td = (x.to(dev, non_blocking=True) for x in tgt_host[ci])
+        s = ref.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, view, proj, deg, campos, False,
+                                              False, c.cx, c.cy)
+        color, normal, depth, opac, _a, _r = ref.GaussianRasterizer(s)(
+            means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
+            rotations=leaf["rotations"], tile_mask=mask)
+        loss = (color - tc).abs().mean() + (depth - td).abs().mean() + 0.1 * (1 - normal[2]).mean()
+        loss.backward()
+        for v in leaf.values():
+            v.grad = None
+        losses.append(loss.item())
+    for i in range(max(3, args.warmup)):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    b.record()
+    torch.cuda.synchronize()
+    ms_e2e = a.elapsed_time(b) / args.steps
+    line = {
+        "impl": "reference", "device": "cuda (unmodified diff-gaussian-surfels compiled for sm_100a, oracle/_ref)",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "%s: %d surfels @%dx%d, SH degree %d, 4 cameras cycled" % (args.workload, P, W, H, deg),
+                   "instances_per_frame": I_mean},
+        "frames_per_s": 1e3 / ms_step, "clocks": clocks,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                         "sample": "full workload; the reference has no CPU implementation of this path, so its own "
+                                   "CUDA build is what is timed here (same GPU, same tensors)"},
+        "e2e": {"value": 256.0 * I_mean / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
+                "frames_per_s": 1e3 / ms_e2e, "h2d_bytes_per_step": 4 * (4 * H * W) + 4 * 35,
+                "d2h_bytes_per_step": 4 + 4 + 8 * 8160,
+                "api": "diff_gaussian_rasterization.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

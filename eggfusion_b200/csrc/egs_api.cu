@@ -1,0 +1,204 @@
+// egs_api.cu -- the extern "C" surface declared in include/eggsplat.h.  Argument checking, workspace carving and
+// kernel sequencing only; no allocation, no device synchronisation, no exceptions.
+#include "egs_common.cuh"
+
+cudaError_t launch_surfel_forward(const egs_frame&, const float*, const float*, const float*, const float*, const float*,
+                                  const float*, const int32_t*, GeomView, ImgView, int32_t*, uint8_t*, cudaStream_t);
+cudaError_t launch_surfel_backward(const egs_frame&, int, int, const float*, const float*, const float*, const float*,
+                                   const float*, const int32_t*, GeomView, const float*, float*, float*, float*, float*,
+                                   float*, float*, float*, float*, cudaStream_t);
+cudaError_t launch_mark_visible(int, const float*, const float*, const float*, uint8_t*, cudaStream_t);
+cudaError_t launch_tile_scan(ImgView, int, long long, cudaStream_t);
+cudaError_t launch_emit_sort(int, int, int, const int32_t*, GeomView, const int32_t*, ImgView, BinView, long long,
+                             cudaStream_t);
+cudaError_t launch_render_forward(const egs_frame&, GeomView, ImgView, BinView, long long, float*, float*, float*,
+                                  float*, cudaStream_t);
+cudaError_t launch_render_backward(const egs_frame&, GeomView, ImgView, BinView, long long, const float*, const float*,
+                                   const float*, const float*, float*, cudaStream_t);
+
+namespace {
+inline int tiles_of(const egs_frame* f, int& gx, int& gy) {
+    gx = (f->width + EGS_TILE - 1) / EGS_TILE;
+    gy = (f->height + EGS_TILE - 1) / EGS_TILE;
+    return gx * gy;
+}
+inline int check_frame(const egs_frame* f) {
+    if (!f || f->num_surfels < 0 || f->width <= 0 || f->height <= 0) return EGS_E_BADARG;
+    if (!f->bg || !f->viewmatrix || !f->projmatrix || !f->campos) return EGS_E_BADARG;
+    if (f->sh_degree < 0 || f->sh_degree > 3) return EGS_E_UNSUPPORTED;
+    return 0;
+}
+#define EGS_TRY(expr)                              \
+    do {                                           \
+        cudaError_t e__ = (expr);                  \
+        if (e__ != cudaSuccess) return (int)e__;   \
+    } while (0)
+
+__global__ void k_export_ranges(ImgView im, int tiles, uint32_t* ranges, int32_t* tile_indices) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tiles) return;
+    const uint32_t a = im.tile_offset[t], b = im.tile_offset[t + 1];
+    if (ranges) {   // the reference memsets ranges to 0 and only touches tiles that own instances
+        ranges[2 * t] = a == b ? 0u : a;
+        ranges[2 * t + 1] = a == b ? 0u : b;
+    }
+    if (tile_indices) tile_indices[t] = im.tile_list[t];
+}
+} // namespace
+
+extern "C" {
+
+EGS_API int egs_abi_version(void) { return EGS_ABI_VERSION; }
+
+EGS_API const char* egs_error_string(int code) {
+    if (code == 0) return "success";
+    if (code == EGS_E_BADARG) return "eggsplat: bad argument";
+    if (code == EGS_E_UNSUPPORTED) return "eggsplat: unsupported configuration";
+    return cudaGetErrorString((cudaError_t)code);
+}
+
+EGS_API int egs_workspace_sizes(int32_t P, int32_t width, int32_t height, int64_t cap_instances, size_t* geom_bytes,
+                        size_t* img_bytes, size_t* bin_bytes) {
+    if (P < 0 || width <= 0 || height <= 0 || cap_instances < 0) return EGS_E_BADARG;
+    const size_t tiles = (size_t)((width + EGS_TILE - 1) / EGS_TILE) * ((height + EGS_TILE - 1) / EGS_TILE);
+    if (geom_bytes) *geom_bytes = carve_geom(nullptr, (size_t)P).bytes;
+    if (img_bytes) *img_bytes = carve_img(nullptr, tiles, (size_t)width * height).bytes;
+    if (bin_bytes) *bin_bytes = carve_bin(nullptr, (size_t)cap_instances).bytes;
+    return 0;
+}
+
+EGS_API int egs_forward_plan(const egs_frame* f, const float* means3D, const float* shs, const float* colors_precomp,
+                     const float* opacities, const float* scales, const float* rotations, const int32_t* tile_mask,
+                     void* geom, void* img, int32_t* radii, uint8_t* active_mask, egs_counters* counters_host,
+                     void* stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    if (!img) return EGS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int gx, gy;
+    const int tiles = tiles_of(f, gx, gy);
+    const int P = f->num_surfels;
+    ImgView im = carve_img(img, (size_t)tiles, (size_t)f->width * f->height);
+    // counters + ticket + tile_count are contiguous at the head of the image workspace
+    EGS_TRY(cudaMemsetAsync(img, 0, (size_t)((char*)im.tile_offset - (char*)img), s));
+    if (P > 0) {
+        if (!means3D || !opacities || !scales || !rotations || !geom || !radii || !active_mask) return EGS_E_BADARG;
+        if (!shs && !colors_precomp) return EGS_E_BADARG;
+        if (!colors_precomp && f->sh_coeffs < (f->sh_degree + 1) * (f->sh_degree + 1)) return EGS_E_BADARG;
+        GeomView g = carve_geom(geom, (size_t)P);
+        EGS_TRY(launch_surfel_forward(*f, means3D, scales, rotations, opacities, shs, colors_precomp, tile_mask, g, im,
+                                      radii, active_mask, s));
+    }
+    EGS_TRY(launch_tile_scan(im, tiles, -1, s));
+    if (counters_host) EGS_TRY(cudaMemcpyAsync(counters_host, im.counters, sizeof(egs_counters), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+EGS_API int egs_forward_render(const egs_frame* f, const int32_t* tile_mask, const int32_t* radii, void* geom, void* img,
+                       void* bin, int64_t cap_instances, float* out_color, float* out_normal, float* out_depth,
+                       float* out_opacity, egs_counters* counters_host, int32_t flags, void* stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    if (!img || !out_color || !out_normal || !out_depth || !out_opacity || cap_instances < 0) return EGS_E_BADARG;
+    if (f->num_surfels > 0 && (!geom || !radii)) return EGS_E_BADARG;
+    if (cap_instances > 0 && !bin) return EGS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int gx, gy;
+    const int tiles = tiles_of(f, gx, gy);
+    const int P = f->num_surfels;
+    ImgView im = carve_img(img, (size_t)tiles, (size_t)f->width * f->height);
+    GeomView g = carve_geom(geom, (size_t)P);
+    BinView bn = carve_bin(bin, (size_t)cap_instances);
+    if (!(flags & EGS_FWD_REUSE_BINNING))
+        EGS_TRY(launch_emit_sort(P, gx, gy, radii, g, tile_mask, im, bn, (long long)cap_instances, s));
+    EGS_TRY(launch_render_forward(*f, g, im, bn, (long long)cap_instances, out_color, out_normal, out_depth,
+                                  out_opacity, s));
+    if (counters_host) EGS_TRY(cudaMemcpyAsync(counters_host, im.counters, sizeof(egs_counters), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+EGS_API int egs_backward_render(const egs_frame* f, const void* geom, const void* img, const void* bin, int64_t cap_instances,
+                        const float* dL_dcolor, const float* dL_dnormal, const float* dL_ddepth,
+                        const float* dL_dopacity, float* screen_grads, int32_t flags, void* stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    const int P = f->num_surfels;
+    if (P == 0) return 0;
+    if (!geom || !img || !dL_dcolor || !dL_dnormal || !dL_ddepth || !dL_dopacity || !screen_grads) return EGS_E_BADARG;
+    if (cap_instances > 0 && !bin) return EGS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int gx, gy;
+    const int tiles = tiles_of(f, gx, gy);
+    ImgView im = carve_img(const_cast<void*>(img), (size_t)tiles, (size_t)f->width * f->height);
+    GeomView g = carve_geom(const_cast<void*>(geom), (size_t)P);
+    BinView bn = carve_bin(const_cast<void*>(bin), (size_t)cap_instances);
+    if (!(flags & EGS_BWD_GRADS_PREZEROED))
+        EGS_TRY(cudaMemsetAsync(screen_grads, 0, sizeof(float) * EGS_SCREEN_GRAD_STRIDE * (size_t)P, s));
+    EGS_TRY(launch_render_backward(*f, g, im, bn, (long long)cap_instances, dL_dcolor, dL_dnormal, dL_ddepth,
+                                   dL_dopacity, screen_grads, s));
+    return 0;
+}
+
+EGS_API int egs_backward_surfels(const egs_frame* f, int32_t first, int32_t count, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* scales, const float* rotations,
+                         const int32_t* radii, const void* geom, const float* screen_grads, float* dL_dmeans3D,
+                         float* dL_dopacity, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dcov3D, void* stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    const int P = f->num_surfels;
+    if (first < 0 || count < 0 || first + count > P) return EGS_E_BADARG;
+    if (count == 0) return 0;
+    if (!means3D || !scales || !rotations || !radii || !geom || !screen_grads) return EGS_E_BADARG;
+    if (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations) return EGS_E_BADARG;
+    if (!colors_precomp && (!shs || !dL_dsh)) return EGS_E_BADARG;
+    GeomView g = carve_geom(const_cast<void*>(geom), (size_t)P);
+    EGS_TRY(launch_surfel_backward(*f, first, count, means3D, shs, colors_precomp, scales, rotations, radii, g,
+                                   screen_grads, dL_dmeans3D, dL_dopacity, dL_dsh, dL_dscales, dL_drotations,
+                                   dL_dmeans2D, dL_dcolors, dL_dcov3D, (cudaStream_t)stream));
+    return 0;
+}
+
+EGS_API int egs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+    if (P < 0) return EGS_E_BADARG;
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !projmatrix || !present) return EGS_E_BADARG;
+    EGS_TRY(launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream));
+    return 0;
+}
+
+EGS_API int egs_debug_export(const egs_frame* f, const void* geom, const void* img, const void* bin, int64_t cap_instances,
+                     uint32_t* point_list, uint32_t* ranges, int32_t* tile_indices, uint32_t* tiles_touched,
+                     uint32_t* n_contrib, float* final_T, float* final_D, float* records, float* cov3D,
+                     uint8_t* clamped, void* stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int gx, gy;
+    const int tiles = tiles_of(f, gx, gy);
+    const size_t P = (size_t)f->num_surfels, N = (size_t)f->width * f->height;
+    ImgView im = carve_img(const_cast<void*>(img), (size_t)tiles, N);
+    const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+    if (ranges || tile_indices) {
+        k_export_ranges<<<(tiles + 255) / 256, 256, 0, s>>>(im, tiles, ranges, tile_indices);
+        EGS_TRY(cudaGetLastError());
+    }
+    if (n_contrib) EGS_TRY(cudaMemcpyAsync(n_contrib, im.n_contrib, 4 * N, d2d, s));
+    if (final_T) EGS_TRY(cudaMemcpyAsync(final_T, im.final_T, 4 * N, d2d, s));
+    if (final_D) EGS_TRY(cudaMemcpyAsync(final_D, im.final_D, 4 * N, d2d, s));
+    if (P > 0 && geom) {
+        GeomView g = carve_geom(const_cast<void*>(geom), P);
+        if (tiles_touched) EGS_TRY(cudaMemcpyAsync(tiles_touched, g.tiles_touched, 4 * P, d2d, s));
+        if (records) EGS_TRY(cudaMemcpyAsync(records, g.rec, sizeof(SplatRecord) * P, d2d, s));
+        if (cov3D) EGS_TRY(cudaMemcpyAsync(cov3D, g.cov3D, 24 * P, d2d, s));
+        if (clamped) EGS_TRY(cudaMemcpyAsync(clamped, g.clamped, P, d2d, s));
+    }
+    if (point_list && bin && cap_instances > 0) {
+        BinView bn = carve_bin(const_cast<void*>(bin), (size_t)cap_instances);
+        EGS_TRY(cudaMemcpyAsync(point_list, bn.point_list, 4 * (size_t)cap_instances, d2d, s));
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,170 @@
+// egs_common.cuh -- shared definitions for the sm_100a surfel rasterizer kernels.
+//
+// HBM layout (all caller-owned, see include/eggsplat.h):
+//   geom workspace, per surfel:   SplatRecord rec[P] (64 B, 16-B aligned quads) | cov3D[P][6] f32 |
+//                                 tiles_touched[P] u32 | clamped[P] u8
+//   img  workspace:               egs_counters (+ticket) | tile_count[T] | tile_offset[T+1] | tile_cursor[T] |
+//                                 tile_list[T] (compacted non-empty tiles) | final_T[N] | final_D[N] | n_contrib[N]
+//   bin  workspace, per instance: keys[cap] u64 (depth bits << 32 | surfel id, bucketed by tile) | point_list[cap] u32
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/eggsplat.h"
+
+#define EGS_TILE 16          // tile edge in pixels (reference: config.h:15-17)
+#define EGS_TILE_THREADS 256 // one thread per pixel of a tile
+
+#if defined(__CUDACC__)
+#define EGS_HD __host__ __device__ __forceinline__
+#else
+#define EGS_HD inline
+#endif
+
+// ---- explicitly rounded fp32 primitives -------------------------------------------------------------------
+// The index-critical chain (cull tests, radii, tile rectangles, depth keys) is written with these so that no
+// compiler is free to contract or re-associate it: the device build uses the *_rn intrinsics, the host build
+// (tests/hostemu) plain IEEE operations compiled with -ffp-contract=off.  The grouping mirrors the FFMA
+// pattern nvcc 12.9 emits for the reference on sm_100a (see oracle/splat_oracle.c header).
+#if defined(__CUDA_ARCH__)
+EGS_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+EGS_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+EGS_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
+EGS_HD float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+EGS_HD float f_div(float a, float b) { return __fdiv_rn(a, b); }
+EGS_HD float f_rcp(float a) { return __frcp_rn(a); }
+EGS_HD float f_sqrt(float a) { return __fsqrt_rn(a); }
+#else
+#include <math.h>
+EGS_HD float f_mul(float a, float b) { return a * b; }
+EGS_HD float f_add(float a, float b) { return a + b; }
+EGS_HD float f_sub(float a, float b) { return a - b; }
+EGS_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+EGS_HD float f_div(float a, float b) { return a / b; }
+EGS_HD float f_rcp(float a) { return 1.0f / a; }
+EGS_HD float f_sqrt(float a) { return sqrtf(a); }
+#endif
+
+// a*b + c*d + e*f : second product rounded on its own, first and third fused
+EGS_HD float f_dot3(float a, float b, float c, float d, float e, float f) {
+    return f_fma(e, f, f_fma(a, b, f_mul(c, d)));
+}
+
+// ---- per-frame constants staged once per CTA --------------------------------------------------------------
+struct FrameConst {
+    float view[16];
+    float proj[16];
+    float campos[3];
+    float bg[3];
+    float tanfovx, tanfovy, fx, fy, cx, cy, mod;
+    int W, H, gx, gy, D, M;
+};
+
+// 64-byte packed splat record: everything the two compositing kernels read per (tile, surfel) instance.
+// q0 is enough for the per-warp bounding-box reject, q0+q1 for alpha, q2+q3 only for contributing pixels.
+struct __align__(16) SplatRecord {
+    float x, y;          // q0: pixel-space centre (means2D)
+    uint32_t ext;        //     conservative half extents of the alpha >= 1/255 ellipse, 2 x u16 in 1/8 px (x | y << 16)
+    float opacity;
+    float cxx, cxy, cyy; // q1: conic
+    float depth;         //     view-space z (also the sort key)
+    float ja, jb;        // q2: plane-depth slope  d(depth)/d(pixel offset)  (Jinv0*u0z+Jinv2*u1z, Jinv1*u0z+Jinv3*u1z)
+    float r, g;
+    float b;             // q3
+    float nx, ny, nz;    //     view-space normal (un-normalised, as the reference blends it)
+};
+static_assert(sizeof(SplatRecord) == 64, "record must be 64 bytes");
+
+// ---- workspace carving --------------------------------------------------------------------------------------
+EGS_HD size_t egs_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct GeomView {
+    SplatRecord* rec;
+    float* cov3D;
+    uint32_t* tiles_touched;
+    uint8_t* clamped;
+    size_t bytes;
+};
+struct ImgView {
+    egs_counters* counters; // followed by ticket words
+    uint32_t* ticket;
+    uint32_t* tile_count;
+    uint32_t* tile_offset; // [T + 1]
+    uint32_t* tile_cursor;
+    int32_t* tile_list;    // [T]
+    float* final_T;
+    float* final_D;
+    uint32_t* n_contrib;
+    size_t bytes;
+};
+struct BinView {
+    unsigned long long* keys;
+    uint32_t* point_list;
+    size_t bytes;
+};
+
+EGS_HD GeomView carve_geom(void* base, size_t P) {
+    GeomView v;
+    size_t o = 0;
+    char* b = (char*)base;
+    v.rec = (SplatRecord*)(b + o);          o = egs_align_up(o + sizeof(SplatRecord) * P, 256);
+    v.cov3D = (float*)(b + o);              o = egs_align_up(o + sizeof(float) * 6 * P, 256);
+    v.tiles_touched = (uint32_t*)(b + o);   o = egs_align_up(o + sizeof(uint32_t) * P, 256);
+    v.clamped = (uint8_t*)(b + o);          o = egs_align_up(o + P, 256);
+    v.bytes = o + 256;
+    return v;
+}
+EGS_HD ImgView carve_img(void* base, size_t tiles, size_t npix) {
+    ImgView v;
+    size_t o = 0;
+    char* b = (char*)base;
+    v.counters = (egs_counters*)(b + o);
+    v.ticket = (uint32_t*)(b + 64);         o = 256;
+    v.tile_count = (uint32_t*)(b + o);      o = egs_align_up(o + 4 * tiles, 256);
+    v.tile_offset = (uint32_t*)(b + o);     o = egs_align_up(o + 4 * (tiles + 1), 256);
+    v.tile_cursor = (uint32_t*)(b + o);     o = egs_align_up(o + 4 * tiles, 256);
+    v.tile_list = (int32_t*)(b + o);        o = egs_align_up(o + 4 * tiles, 256);
+    v.final_T = (float*)(b + o);            o = egs_align_up(o + 4 * npix, 256);
+    v.final_D = (float*)(b + o);            o = egs_align_up(o + 4 * npix, 256);
+    v.n_contrib = (uint32_t*)(b + o);       o = egs_align_up(o + 4 * npix, 256);
+    v.bytes = o + 256;
+    return v;
+}
+EGS_HD BinView carve_bin(void* base, size_t cap) {
+    BinView v;
+    size_t o = 0;
+    char* b = (char*)base;
+    v.keys = (unsigned long long*)(b + o);  o = egs_align_up(o + 8 * cap, 256);
+    v.point_list = (uint32_t*)(b + o);      o = egs_align_up(o + 4 * cap, 256);
+    v.bytes = o + 256;
+    return v;
+}
+
+// getRect of the reference (auxiliary.h:47-57): float arithmetic, truncation toward zero, clamped to the grid.
+EGS_HD void egs_tile_rect(float px, float py, int radius, int gx, int gy, int& x0, int& y0, int& x1, int& y1) {
+    const float r = (float)radius;
+    int a;
+    a = (int)f_mul(f_sub(px, r), 0.0625f);                                   x0 = a < 0 ? 0 : (a > gx ? gx : a);
+    a = (int)f_mul(f_sub(py, r), 0.0625f);                                   y0 = a < 0 ? 0 : (a > gy ? gy : a);
+    a = (int)f_mul(f_sub(f_add(f_add(px, r), 16.0f), 1.0f), 0.0625f);        x1 = a < 0 ? 0 : (a > gx ? gx : a);
+    a = (int)f_mul(f_sub(f_add(f_add(py, r), 16.0f), 1.0f), 0.0625f);        y1 = a < 0 ? 0 : (a > gy ? gy : a);
+}
+
+#if defined(__CUDACC__)
+// Stage the per-frame constants into shared memory (one pass, first 64 threads).
+__device__ __forceinline__ void load_frame_const(FrameConst& fc, const egs_frame& f) {
+    const int t = threadIdx.x;
+    if (t < 16) fc.view[t] = __ldg(f.viewmatrix + t);
+    else if (t < 32) fc.proj[t - 16] = __ldg(f.projmatrix + t - 16);
+    else if (t < 35) fc.campos[t - 32] = __ldg(f.campos + t - 32);
+    else if (t < 38) fc.bg[t - 35] = __ldg(f.bg + t - 35);
+    else if (t == 38) {
+        fc.tanfovx = f.tanfovx; fc.tanfovy = f.tanfovy;
+        fc.fy = f.height / (2.0f * f.tanfovy);   // rasterizer_impl.cu:244-245
+        fc.fx = f.width / (2.0f * f.tanfovx);
+        fc.cx = f.cx; fc.cy = f.cy; fc.mod = f.scale_modifier;
+        fc.W = f.width; fc.H = f.height;
+        fc.gx = (f.width + EGS_TILE - 1) / EGS_TILE; fc.gy = (f.height + EGS_TILE - 1) / EGS_TILE;
+        fc.D = f.sh_degree; fc.M = f.sh_coeffs;
+    }
+}
+#endif

@@ -1,0 +1,164 @@
+// egs_preprocess.cu -- per-surfel kernels: forward projection (+ per-tile instance counting), per-surfel backward,
+// and the coarse visibility test.  One thread per surfel, 256-thread CTAs, per-frame constants staged in smem.
+//
+// Replaces preprocessCUDA<3> (DGS/cuda_rasterizer/forward.cu:158-301), computeCov2DCUDA + preprocessCUDA<3> (bwd)
+// (DGS/cuda_rasterizer/backward.cu:144-416) and checkFrustum (DGS/cuda_rasterizer/rasterizer_impl.cu:54-66).
+#include "egs_surfel_math.cuh"
+
+__global__ void __launch_bounds__(256)
+k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
+                 const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
+                 const float* __restrict__ colors, const int32_t* __restrict__ tile_mask, GeomView g, ImgView im,
+                 int32_t* __restrict__ radii, uint8_t* __restrict__ active) {
+    __shared__ FrameConst fc;
+    load_frame_const(fc, f);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < f.num_surfels;
+    bool visible = false;
+    if (valid) {
+        SurfelFwd o;
+        const bool use_sh = colors == nullptr;
+        const float* csrc = use_sh ? shs + (size_t)3 * fc.M * i : colors + (size_t)3 * i;
+        surfel_forward(fc, means + (size_t)3 * i, scales + (size_t)3 * i, rots + (size_t)4 * i, __ldg(opac + i), csrc,
+                       use_sh, o);
+        radii[i] = o.radius;
+        active[i] = (uint8_t)o.active;
+        uint32_t cnt = 0;
+        if (o.radius > 0) {
+            visible = true;
+            float4* dst = reinterpret_cast<float4*>(g.rec + i);
+            const float4* src = reinterpret_cast<const float4*>(&o.rec);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            float2* c2 = reinterpret_cast<float2*>(g.cov3D + (size_t)6 * i);
+            c2[0] = make_float2(o.cov3D[0], o.cov3D[1]);
+            c2[1] = make_float2(o.cov3D[2], o.cov3D[3]);
+            c2[2] = make_float2(o.cov3D[4], o.cov3D[5]);
+            g.clamped[i] = (uint8_t)o.clamped;
+            // per-tile instance counts: the histogram that replaces the reference's per-surfel scan
+            for (int y = o.y0; y < o.y1; y++)
+                for (int x = o.x0; x < o.x1; x++) {
+                    const int t = y * fc.gx + x;
+                    if (tile_mask == nullptr || __ldg(tile_mask + t) != 0) {
+                        atomicAdd(im.tile_count + t, 1u);
+                        cnt++;
+                    }
+                }
+        }
+        g.tiles_touched[i] = cnt;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, visible);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&im.counters->num_visible, __popc(ballot));
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(256)
+k_surfel_backward(const egs_frame f, int first, int count, const float* __restrict__ means,
+                  const float* __restrict__ shs, const float* __restrict__ colors, const float* __restrict__ scales,
+                  const float* __restrict__ rots, const int32_t* __restrict__ radii, GeomView g,
+                  const float* __restrict__ sg, float* __restrict__ d_means, float* __restrict__ d_opacity,
+                  float* __restrict__ d_sh, float* __restrict__ d_scales, float* __restrict__ d_rots,
+                  float* __restrict__ d_means2D, float* __restrict__ d_colors, float* __restrict__ d_cov3D) {
+    __shared__ FrameConst fc;
+    load_frame_const(fc, f);
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = first + k;
+    const int M = fc.M;
+    const bool use_sh = colors == nullptr;
+    float g16[16];
+    SurfelBwd o;
+    const bool vis = radii[i] > 0;
+    float* my_sh = use_sh ? d_sh + (size_t)3 * M * i : nullptr;
+    if (vis) {
+        const float4* row = reinterpret_cast<const float4*>(sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 v = __ldg(row + q);
+            g16[4 * q] = v.x; g16[4 * q + 1] = v.y; g16[4 * q + 2] = v.z; g16[4 * q + 3] = v.w;
+        }
+        const float* mean = means + (size_t)3 * i;
+        surfel_backward_geom(fc, mean, scales + (size_t)3 * i, rots + (size_t)4 * i, g.cov3D + (size_t)6 * i, g16, o);
+        if (use_sh) {
+            const float dir[3] = {mean[0] - fc.campos[0], mean[1] - fc.campos[1], mean[2] - fc.campos[2]};
+            const float gcol[3] = {g16[6], g16[7], g16[8]};
+            float add[3];
+            const int used = (fc.D + 1) * (fc.D + 1);
+            sh_backward(fc.D, shs + (size_t)3 * M * i, dir, (uint32_t)g.clamped[i], gcol,
+                        [my_sh](int kk, int ch, float v) { my_sh[3 * kk + ch] = v; }, add);
+            for (int kk = 3 * used; kk < 3 * M; kk++) my_sh[kk] = 0.f; // coefficients above the active degree
+            o.d_mean[0] += add[0]; o.d_mean[1] += add[1]; o.d_mean[2] += add[2];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) g16[q] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { o.d_mean[q] = 0.f; o.d_scale[q] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) o.d_rot[q] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 6; q++) o.d_cov3D[q] = 0.f;
+        if (use_sh)
+            for (int kk = 0; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+    }
+    d_means[3 * (size_t)i] = o.d_mean[0]; d_means[3 * (size_t)i + 1] = o.d_mean[1]; d_means[3 * (size_t)i + 2] = o.d_mean[2];
+    d_scales[3 * (size_t)i] = o.d_scale[0]; d_scales[3 * (size_t)i + 1] = o.d_scale[1]; d_scales[3 * (size_t)i + 2] = o.d_scale[2];
+    reinterpret_cast<float4*>(d_rots)[i] = make_float4(o.d_rot[0], o.d_rot[1], o.d_rot[2], o.d_rot[3]);
+    d_opacity[i] = g16[5];
+    if (d_means2D) { d_means2D[3 * (size_t)i] = g16[0]; d_means2D[3 * (size_t)i + 1] = g16[1]; d_means2D[3 * (size_t)i + 2] = 0.f; }
+    if (d_colors) { d_colors[3 * (size_t)i] = g16[6]; d_colors[3 * (size_t)i + 1] = g16[7]; d_colors[3 * (size_t)i + 2] = g16[8]; }
+    if (d_cov3D) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) d_cov3D[6 * (size_t)i + q] = o.d_cov3D[q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ markVisible
+__global__ void __launch_bounds__(256)
+k_mark_visible(int P, const float* __restrict__ means, const float* __restrict__ view, const float* __restrict__ proj,
+               uint8_t* __restrict__ present) {
+    __shared__ float sv[16], sp[16];
+    if (threadIdx.x < 16) sv[threadIdx.x] = view[threadIdx.x];
+    else if (threadIdx.x < 32) sp[threadIdx.x - 16] = proj[threadIdx.x - 16];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float x = means[3 * (size_t)i], y = means[3 * (size_t)i + 1], z = means[3 * (size_t)i + 2];
+    const float hx = xf_affine(sp, 0, x, y, z), hy = xf_affine(sp, 1, x, y, z), hw = xf_affine(sp, 3, x, y, z);
+    const float pw = f_rcp(f_add(hw, 0.0000001f));
+    const float ndx = f_mul(hx, pw), ndy = f_mul(hy, pw);
+    const float vz = xf_affine(sv, 2, x, y, z);
+    // auxiliary.h:168: the +-1.3 literals are doubles
+    present[i] = !(vz <= 0.2f || (double)ndx < -1.3 || (double)ndx > 1.3 || (double)ndy < -1.3 || (double)ndy > 1.3);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const float* scales, const float* rots,
+                                  const float* opac, const float* shs, const float* colors, const int32_t* tile_mask,
+                                  GeomView g, ImgView im, int32_t* radii, uint8_t* active, cudaStream_t s) {
+    const int P = f.num_surfels;
+    if (P == 0) return cudaSuccess;
+    k_surfel_forward<<<(P + 255) / 256, 256, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im, radii,
+                                                     active);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_surfel_backward(const egs_frame& f, int first, int count, const float* means, const float* shs,
+                                   const float* colors, const float* scales, const float* rots, const int32_t* radii,
+                                   GeomView g, const float* sg, float* d_means, float* d_opacity, float* d_sh,
+                                   float* d_scales, float* d_rots, float* d_means2D, float* d_colors, float* d_cov3D,
+                                   cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    k_surfel_backward<<<(count + 255) / 256, 256, 0, s>>>(f, first, count, means, shs, colors, scales, rots, radii, g,
+                                                          sg, d_means, d_opacity, d_sh, d_scales, d_rots, d_means2D,
+                                                          d_colors, d_cov3D);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mark_visible(int P, const float* means, const float* view, const float* proj, uint8_t* present,
+                                cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    k_mark_visible<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, proj, present);
+    return cudaGetLastError();
+}

@@ -1,0 +1,235 @@
+// egs_render_bwd.cu -- reverse compositing walk: per-pixel gradients -> per-surfel screen-space gradients.
+//
+// Replaces renderCUDA<3> backward (DGS/cuda_rasterizer/backward.cu:419-676), which issues 13 float atomicAdds
+// per contributing (pixel, surfel) pair.  Here:
+//   * a warp owns an 8x4 pixel block and skips a splat whose alpha >= 1/255 ellipse cannot reach the block;
+//   * the 13 partials of the 32 pixels of a warp are summed with a transposing butterfly (16 shuffles; after it
+//     lane 2v holds the warp total of value v) instead of 13 x 5 shuffle-reduces;
+//   * the (at most 8) warp totals of a splat are combined through shared memory and leave the CTA as four
+//     16-byte vector reductions (red.global.add.v4.f32) into the [P][16] screen-gradient block: <= 4 vector
+//     atomics per (tile, surfel) instead of 13 scalar atomics per (pixel, surfel);
+//   * the walk starts at the CTA-wide maximum of n_contrib, skipping list tails nobody blended.
+// The per-pair arithmetic follows the reference, including its deviations from the exact derivative:
+// x10 on the per-surfel normal gradient, the un-weighted depth-differencing term on mean2D (SURVEY 8 a-bis).
+#include "egs_common.cuh"
+
+#define BWD_BATCH 64
+#define BWD_WARPS (EGS_TILE_THREADS / 32)
+
+__device__ __forceinline__ float conic_power_b(float cxx, float cxy, float cyy, float dx, float dy) {
+    const float q = __fmaf_rn(__fmul_rn(cxx, dx), dx, __fmul_rn(__fmul_rn(cyy, dy), dy));
+    const float dist = __fmaf_rn(__fmul_rn(__fmul_rn(2.f, cxy), dx), dy, q);
+    return __fmul_rn(-0.5f, dist);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// After this, lane L holds in v[0] the sum over the warp of the callers' v[L >> 1].
+__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
+    const unsigned full = 0xffffffffu;
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float send = hi ? v[i] : v[i + 8];
+            const float keep = hi ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = hi ? v[i] : v[i + 4];
+            const float keep = hi ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = hi ? v[i] : v[i + 2];
+            const float keep = hi ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(full, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+}
+
+__global__ void __launch_bounds__(EGS_TILE_THREADS)
+k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
+                  BinView bn, long long cap, const float* __restrict__ gC, const float* __restrict__ gN,
+                  const float* __restrict__ gDp, const float* __restrict__ gOp, float* __restrict__ sg) {
+    __shared__ float4 s_rec[BWD_BATCH * 4];
+    __shared__ uint32_t s_id[BWD_BATCH];
+    __shared__ __align__(16) float s_part[BWD_WARPS][BWD_BATCH][16];
+    __shared__ unsigned long long s_mask[BWD_WARPS];
+    __shared__ int s_top;
+
+    const int tile = blockIdx.x;
+    const long long start = im.tile_offset[tile];
+    long long end = im.tile_offset[tile + 1];
+    if (end > cap) end = cap;
+    const int n = (int)(end - start);
+    if (n <= 0) return;
+
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = tx * EGS_TILE + (warp & 1) * 8, by = ty * EGS_TILE + (warp >> 1) * 4;
+    const int px = bx + (lane & 7), py = by + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)W * py + px;
+    const uint32_t* __restrict__ plist = bn.point_list + start;
+    const float pxf = (float)px, pyf = (float)py;
+    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;
+
+    if (threadIdx.x == 0) s_top = 0;
+    __syncthreads();
+
+    float T_final = 0.f, D_final = 0.f;
+    int last_contributor = 0;
+    float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gn0 = 0.f, gn1 = 0.f, gn2 = 0.f, gD = 0.f, gO = 0.f;
+    if (inside) {
+        T_final = im.final_T[pix];
+        D_final = im.final_D[pix];
+        last_contributor = (int)im.n_contrib[pix];
+        gc0 = __ldg(gC + pix); gc1 = __ldg(gC + HW + pix); gc2 = __ldg(gC + 2 * HW + pix);
+        gn0 = __ldg(gN + pix); gn1 = __ldg(gN + HW + pix); gn2 = __ldg(gN + 2 * HW + pix);
+        gD = __ldg(gDp + pix);
+        gO = __ldg(gOp + pix);
+    }
+    {
+        int wmax = last_contributor;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+        if (lane == 0 && wmax > 0) atomicMax(&s_top, wmax);
+    }
+    __syncthreads();
+    const int top0 = s_top;
+
+    // per-pixel constants of the depth term (backward.cu:620-621), same evaluation order as the reference
+    const float one_m_Tf = 1.f - T_final;
+    const float gDn = gD / one_m_Tf;
+    const float kdepth = gD * D_final / one_m_Tf / one_m_Tf * -T_final;
+    const float bg_dot = __ldg(bg) * gc0 + __ldg(bg + 1) * gc1 + __ldg(bg + 2) * gc2;
+    const float ddelx = 0.5f * (float)W, ddely = 0.5f * (float)H;
+
+    float T = T_final;
+    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f, acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f, acc_d = 0.f;
+    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f, last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f,
+          last_d = 0.f;
+
+    for (int top = top0; top > 0; top -= BWD_BATCH) {
+        const int m = min(BWD_BATCH, top);
+        __syncthreads(); // previous batch fully combined before its staging buffers are reused
+        if ((int)threadIdx.x < m) {
+            const uint32_t id = __ldg(plist + (top - 1 - (int)threadIdx.x));
+            s_id[threadIdx.x] = id;
+            const float4* src = reinterpret_cast<const float4*>(rec + id);
+            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+            s_rec[threadIdx.x * 4] = a; s_rec[threadIdx.x * 4 + 1] = b;
+            s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
+        }
+        __syncthreads();
+
+        unsigned long long wmask = 0ull;
+        for (int j = 0; j < m; j++) {
+            const int pos = top - 1 - j; // index in the tile list == the reference's `contributor`
+            const float4 q0 = s_rec[4 * j];
+            const uint32_t ext = __float_as_uint(q0.z);
+            const float hx = (float)(ext & 0xffffu) * 0.125f, hy = (float)(ext >> 16) * 0.125f;
+            if (fabsf(q0.x - bcx) > hx + 3.5f || fabsf(q0.y - bcy) > hy + 1.5f) continue; // warp-uniform
+            const float4 q1 = s_rec[4 * j + 1];
+            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
+            const float power = conic_power_b(q1.x, q1.y, q1.z, dx, dy);
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, __fmul_rn(q0.w, G));
+            const bool act = pos < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (!__any_sync(0xffffffffu, act)) continue;
+
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = 0.f;
+            if (act) {
+                const float4 q2 = s_rec[4 * j + 2], q3 = s_rec[4 * j + 3];
+                const float one_m_a = 1.f - alpha;
+                T = T / one_m_a;
+                const float w = alpha * T;
+                const float ra = 1.f / one_m_a;
+                float dL_dalpha;
+                {   // colour (backward.cu:577-591)
+                    const float one_m_la = 1.f - last_alpha;
+                    acc_c0 = last_alpha * last_c0 + one_m_la * acc_c0; last_c0 = q2.z;
+                    acc_c1 = last_alpha * last_c1 + one_m_la * acc_c1; last_c1 = q2.w;
+                    acc_c2 = last_alpha * last_c2 + one_m_la * acc_c2; last_c2 = q3.x;
+                    dL_dalpha = (q2.z - acc_c0) * gc0 + (q2.w - acc_c1) * gc1 + (q3.x - acc_c2) * gc2;
+                    v[6] = w * gc0; v[7] = w * gc1; v[8] = w * gc2;
+                    // normal (backward.cu:593-606): x10 on the per-surfel gradient only
+                    acc_n0 = last_alpha * last_n0 + one_m_la * acc_n0; last_n0 = q3.y;
+                    acc_n1 = last_alpha * last_n1 + one_m_la * acc_n1; last_n1 = q3.z;
+                    acc_n2 = last_alpha * last_n2 + one_m_la * acc_n2; last_n2 = q3.w;
+                    dL_dalpha += (q3.y - acc_n0) * gn0 + (q3.z - acc_n1) * gn1 + (q3.w - acc_n2) * gn2;
+                    v[9] = w * gn0 * 10.f; v[10] = w * gn1 * 10.f; v[11] = w * gn2 * 10.f;
+                    // plane-corrected depth (backward.cu:609-627)
+                    const float d_cur = q1.w - (dx * q2.x + dy * q2.y);
+                    acc_d = last_alpha * last_d + one_m_la * acc_d; last_d = d_cur;
+                    dL_dalpha += kdepth * ra / T + (d_cur - acc_d) * gDn;
+                    v[12] = w * gDn;
+                }
+                dL_dalpha *= T;
+                dL_dalpha += gO * T_final * ra;       // opacity image (backward.cu:631)
+                last_alpha = alpha;
+                dL_dalpha += (-T_final * ra) * bg_dot; // background (backward.cu:638-641)
+                const float dL_ddist = dL_dalpha * q0.w * -0.5f * G;
+                v[0] = dL_ddist * 2.f * (q1.x * dx + q1.y * dy) * ddelx - gD * q2.x; // backward.cu:648-660
+                v[1] = dL_ddist * 2.f * (q1.z * dy + q1.y * dx) * ddely - gD * q2.y;
+                v[2] = dL_ddist * (dx * dx);
+                v[3] = dL_ddist * (dx * dy);
+                v[4] = dL_ddist * (dy * dy);
+                v[5] = G * dL_dalpha;
+            }
+            warp_transpose_reduce16(v, lane);
+            if (!(lane & 1)) s_part[warp][j][lane >> 1] = v[0];
+            wmask |= 1ull << j;
+        }
+        if (lane == 0) s_mask[warp] = wmask;
+        __syncthreads();
+
+        // combine the warps' totals: thread -> (record, quad); one 16-byte vector reduction per quad
+        {
+            const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+            if (r < m) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool any = false;
+#pragma unroll
+                for (int wv = 0; wv < BWD_WARPS; wv++) {
+                    if (s_mask[wv] >> r & 1ull) {
+                        const float4 p = *reinterpret_cast<const float4*>(&s_part[wv][r][4 * q]);
+                        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+                        any = true;
+                    }
+                }
+                if (any) red_add_v4(sg + (size_t)EGS_SCREEN_GRAD_STRIDE * s_id[r] + 4 * q, s.x, s.y, s.z, s.w);
+            }
+        }
+    }
+}
+
+cudaError_t launch_render_backward(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
+                                   const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
+                                   cudaStream_t s) {
+    const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
+    k_render_backward<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, gC, gN, gD,
+                                                           gO, sg);
+    return cudaGetLastError();
+}

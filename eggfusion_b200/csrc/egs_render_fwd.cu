@@ -1,0 +1,117 @@
+// egs_render_fwd.cu -- front-to-back compositing of colour / normal / plane-corrected depth / opacity.
+//
+// Replaces renderCUDA<3> forward (DGS/cuda_rasterizer/forward.cu:306-497).  Differences in organisation, not in
+// results:
+//   * one CTA per tile of the WHOLE grid: tiles with an empty list write zeros (the reference leaves its
+//     zero-initialised outputs untouched there), so no memset and no host-side tile compaction is needed;
+//   * a warp owns an 8x4 pixel block (full 32-byte sectors on every image row it writes) and rejects a splat
+//     for the whole block with one shared-memory quad read when its alpha >= 1/255 ellipse cannot reach the block;
+//   * splats are staged as packed 64-byte records (one gather per instance instead of eight).
+// Per pixel the arithmetic order of the reference is kept: power, alpha = min(0.99, o*exp(power)), skip < 1/255,
+// stop (without blending) when T(1-alpha) < 1e-4, w = alpha*T, fma accumulation, T clamp at 1-1e-6.
+#include "egs_common.cuh"
+
+#define FWD_BATCH 256
+
+__device__ __forceinline__ float conic_power(float cxx, float cxy, float cyy, float dx, float dy) {
+    // (cxx*dx*dx + cyy*dy*dy) + 2*cxy*dx*dy, grouped as nvcc contracts the reference expression
+    const float q = __fmaf_rn(__fmul_rn(cxx, dx), dx, __fmul_rn(__fmul_rn(cyy, dy), dy));
+    const float dist = __fmaf_rn(__fmul_rn(__fmul_rn(2.f, cxy), dx), dy, q);
+    return __fmul_rn(-0.5f, dist);
+}
+
+__global__ void __launch_bounds__(EGS_TILE_THREADS)
+k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
+                 BinView bn, long long cap, float* __restrict__ out_color, float* __restrict__ out_normal,
+                 float* __restrict__ out_depth, float* __restrict__ out_opac) {
+    __shared__ float4 s_rec[FWD_BATCH * 4];
+
+    const int tile = blockIdx.x;
+    const int tx = tile % gx, ty = tile / gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = tx * EGS_TILE + (warp & 1) * 8, by = ty * EGS_TILE + (warp >> 1) * 4;
+    const int px = bx + (lane & 7), py = by + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)W * py + px;
+
+    const long long start = im.tile_offset[tile];
+    long long end = im.tile_offset[tile + 1];
+    if (end > cap) end = cap;
+    const int n = (int)(end - start);
+    if (n <= 0) {
+        if (inside) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) { out_color[ch * HW + pix] = 0.f; out_normal[ch * HW + pix] = 0.f; }
+            out_depth[pix] = 0.f;
+            out_opac[pix] = 0.f;
+        }
+        return;
+    }
+    const uint32_t* __restrict__ plist = bn.point_list + start;
+    const float pxf = (float)px, pyf = (float)py;
+    // centre and half size of this warp's pixel block, for the bounding-box reject
+    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f;
+    uint32_t last = 0;
+    bool done = !inside;
+
+    for (int base = 0; base < n; base += FWD_BATCH) {
+        if (__syncthreads_count(done) == EGS_TILE_THREADS) break;
+        const int m = min(FWD_BATCH, n - base);
+        if ((int)threadIdx.x < m) {
+            const uint32_t id = __ldg(plist + base + threadIdx.x);
+            const float4* src = reinterpret_cast<const float4*>(rec + id);
+            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+            s_rec[threadIdx.x * 4] = a; s_rec[threadIdx.x * 4 + 1] = b;
+            s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
+        }
+        __syncthreads();
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int j = 0; j < m; j++) {
+            const float4 q0 = s_rec[4 * j];
+            const uint32_t ext = __float_as_uint(q0.z);
+            const float hx = (float)(ext & 0xffffu) * 0.125f, hy = (float)(ext >> 16) * 0.125f;
+            if (fabsf(q0.x - bcx) > hx + 3.5f || fabsf(q0.y - bcy) > hy + 1.5f) continue; // warp-uniform
+            if (done) continue;
+            const float4 q1 = s_rec[4 * j + 1];
+            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
+            const float power = conic_power(q1.x, q1.y, q1.z, dx, dy);
+            if (power > 0.0f) continue;
+            const float alpha = fminf(0.99f, __fmul_rn(q0.w, expf(power)));
+            if (alpha < 1.0f / 255.0f) continue;
+            const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+            if (test_T < 0.0001f) { done = true; continue; }
+            const float w = __fmul_rn(alpha, T);
+            const float4 q2 = s_rec[4 * j + 2], q3 = s_rec[4 * j + 3];
+            const float dj = q1.w - (dx * q2.x + dy * q2.y);
+            D = fmaf(dj, w, D);
+            C0 = fmaf(q2.z, w, C0); C1 = fmaf(q2.w, w, C1); C2 = fmaf(q3.x, w, C2);
+            N0 = fmaf(q3.y, w, N0); N1 = fmaf(q3.z, w, N1); N2 = fmaf(q3.w, w, N2);
+            T = test_T;
+            last = (uint32_t)(base + j + 1);
+        }
+    }
+    if (inside) {
+        T = fminf(0.999999f, T);
+        im.final_T[pix] = T;
+        im.final_D[pix] = D;
+        im.n_contrib[pix] = last;
+        out_color[pix] = fmaf(T, __ldg(bg), C0);
+        out_color[HW + pix] = fmaf(T, __ldg(bg + 1), C1);
+        out_color[2 * HW + pix] = fmaf(T, __ldg(bg + 2), C2);
+        out_normal[pix] = N0; out_normal[HW + pix] = N1; out_normal[2 * HW + pix] = N2;
+        out_depth[pix] = D / (1.f - T);
+        out_opac[pix] = 1.f - T;
+    }
+}
+
+cudaError_t launch_render_forward(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
+                                  float* out_color, float* out_normal, float* out_depth, float* out_opac,
+                                  cudaStream_t s) {
+    const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
+    k_render_forward<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, out_color,
+                                                          out_normal, out_depth, out_opac);
+    return cudaGetLastError();
+}

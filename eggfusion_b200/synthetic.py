@@ -1,0 +1,190 @@
+"""Synthetic surfel scenes and cameras (numpy only, deterministic).
+
+Implements the "layers" scene of SURVEY.md section 8(d): P/L surfels on each of L smooth depth sheets seen by a
+pinhole camera, the way EGG-Fusion seeds surfels from a depth frame
+(/root/reference/src/core/mapper.py:446-492, /root/reference/src/core/gaussian_surfels.py:169-222).
+Camera conventions follow /root/reference/src/utils/frame.py:159-169 (viewmatrix = W2C^T,
+projmatrix = (P @ W2C)^T) and /root/reference/src/utils/camera_utils.py:100-120 (getProjectionMatrix_v2).
+The same arrays feed the reference, the CPU oracle and the CUDA path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SEED = 20251201
+SH_C0 = 0.28209479177387814
+
+
+@dataclass
+class Camera:
+    """Everything GaussianRasterizationSettings needs, as numpy / python scalars."""
+
+    width: int
+    height: int
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+    w2c: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    znear: float = 0.01
+    zfar: float = 100.0
+
+    @property
+    def fovx(self) -> float:
+        return 2.0 * math.atan(self.width / (2.0 * self.fx))
+
+    @property
+    def fovy(self) -> float:
+        return 2.0 * math.atan(self.height / (2.0 * self.fy))
+
+    @property
+    def tanfovx(self) -> float:
+        return math.tan(self.fovx * 0.5)
+
+    @property
+    def tanfovy(self) -> float:
+        return math.tan(self.fovy * 0.5)
+
+    def projection(self) -> np.ndarray:
+        """getProjectionMatrix_v2 (camera_utils.py:100-120), fp32 like the reference's torch.zeros(4, 4)."""
+        ty, tx = math.tan(self.fovy / 2), math.tan(self.fovx / 2)
+        top, right = ty * self.znear, tx * self.znear
+        P = np.zeros((4, 4), dtype=np.float32)
+        P[0, 0] = 2.0 * self.znear / (2 * right)
+        P[1, 1] = 2.0 * self.znear / (2 * top)
+        P[3, 2] = 1.0
+        P[2, 2] = self.zfar / (self.zfar - self.znear)
+        P[2, 3] = -(self.zfar * self.znear) / (self.zfar - self.znear)
+        return P
+
+    @property
+    def viewmatrix(self) -> np.ndarray:
+        """world_view_transform = W2C^T (frame.py:159-161), contiguous fp32 [4,4]."""
+        return np.ascontiguousarray(self.w2c.astype(np.float32).T)
+
+    @property
+    def projmatrix(self) -> np.ndarray:
+        """full_proj_transform = W2C^T @ P^T (frame.py:163-165, dataset.py:37-44)."""
+        return np.ascontiguousarray((self.viewmatrix @ self.projection().T).astype(np.float32))
+
+    @property
+    def campos(self) -> np.ndarray:
+        """camera_center = inverse(W2C^T)[3, :3] (frame.py:167-169)."""
+        return np.ascontiguousarray(np.linalg.inv(self.viewmatrix.astype(np.float64))[3, :3].astype(np.float32))
+
+    @property
+    def tiles(self) -> tuple[int, int]:
+        return ((self.height + 15) // 16, (self.width + 15) // 16)
+
+
+def default_camera(width: int, height: int, w2c: np.ndarray | None = None) -> Camera:
+    """fx = fy = 0.9 W, principal point at the image centre."""
+    f = 0.9 * width
+    cam = Camera(width, height, f, f, (width - 1) / 2.0, (height - 1) / 2.0)
+    if w2c is not None:
+        cam.w2c = np.asarray(w2c, dtype=np.float32)
+    return cam
+
+
+def look_from(offset_xyz=(0.0, 0.0, 0.0), yaw=0.0, pitch=0.0) -> np.ndarray:
+    """A W2C matrix for a camera displaced by `offset_xyz` and rotated by small yaw/pitch (radians)."""
+    cy_, sy_ = math.cos(yaw), math.sin(yaw)
+    cp_, sp_ = math.cos(pitch), math.sin(pitch)
+    Ry = np.array([[cy_, 0, sy_], [0, 1, 0], [-sy_, 0, cy_]])
+    Rx = np.array([[1, 0, 0], [0, cp_, -sp_], [0, sp_, cp_]])
+    R = Rx @ Ry
+    c2w = np.eye(4)
+    c2w[:3, :3] = R.T
+    c2w[:3, 3] = np.asarray(offset_xyz, dtype=np.float64)
+    return np.linalg.inv(c2w).astype(np.float32)
+
+
+def _quat_z_to(n: np.ndarray) -> np.ndarray:
+    """Unit quaternion (w,x,y,z) rotating +z onto unit vectors n [P,3]
+    (compute_rot / quaternion_from_axis_angle, /root/reference/src/core/utils.py:114-127)."""
+    z = np.array([0.0, 0.0, 1.0])
+    axis = np.cross(np.broadcast_to(z, n.shape), n)
+    axis = axis / (np.linalg.norm(axis, axis=-1, keepdims=True) + 1e-8)
+    ang = np.arccos(np.clip(n[:, 2], -1.0, 1.0))[:, None]
+    q = np.concatenate([np.cos(ang / 2), axis * np.sin(ang / 2)], axis=1)
+    q = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    return q.astype(np.float32)
+
+
+def make_scene(P: int, cam: Camera, layers: int = 4, sh_degree: int = 3, seed: int = SEED,
+               normal_jitter: float = 0.15) -> dict[str, np.ndarray]:
+    """Surfels on `layers` depth sheets in the frame of a canonical (identity-pose) camera with cam's intrinsics.
+
+    Returns post-activation tensors exactly as Renderer.render feeds them to the rasterizer
+    (/root/reference/src/core/mapper.py:565-585): xyz [P,3], opacity [P,1], shs [P,M,3],
+    scales [P,3] (z = 0), rotations [P,4] (w,x,y,z, unit).
+    """
+    rng = np.random.default_rng(seed)
+    W, H = cam.width, cam.height
+    M = (sh_degree + 1) ** 2
+    layer = rng.integers(0, layers, size=P)
+    u = rng.uniform(-0.05 * W, 1.05 * W, size=P)
+    v = rng.uniform(-0.05 * H, 1.05 * H, size=P)
+    un, vn = u / W, v / H
+    z = 1.5 + 0.6 * layer + 0.3 * np.sin(3 * un) * np.cos(2 * vn)
+    x = (u - cam.cx) * z / cam.fx
+    y = (v - cam.cy) * z / cam.fy
+    xyz = np.stack([x, y, z], axis=1)
+
+    # sheet normal from the analytic surface gradient, jittered, flipped towards the camera
+    dz_du = 0.3 * 3 * np.cos(3 * un) * np.cos(2 * vn) / W
+    dz_dv = -0.3 * 2 * np.sin(3 * un) * np.sin(2 * vn) / H
+    tu = np.stack([z / cam.fx + (u - cam.cx) / cam.fx * dz_du, (v - cam.cy) / cam.fy * dz_du, dz_du], axis=1)
+    tv = np.stack([(u - cam.cx) / cam.fx * dz_dv, z / cam.fy + (v - cam.cy) / cam.fy * dz_dv, dz_dv], axis=1)
+    n = np.cross(tu, tv)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    n += rng.normal(0.0, normal_jitter, size=n.shape)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    flip = np.sum(n * xyz, axis=1) > 0
+    n[flip] *= -1.0
+    rotations = _quat_z_to(n)
+
+    r_px = rng.uniform(1.0, 3.0, size=P)
+    scales = np.stack([r_px * z / cam.fx, r_px * z / cam.fy, np.zeros(P)], axis=1)
+    opacity = rng.uniform(0.3, 0.99, size=(P, 1))
+    shs = np.zeros((P, M, 3))
+    shs[:, 0, :] = (rng.uniform(0.0, 1.0, size=(P, 3)) - 0.5) / SH_C0
+    if M > 1:
+        shs[:, 1:, :] = rng.normal(0.0, 0.05, size=(P, M - 1, 3))
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return {"xyz": f32(xyz), "opacity": f32(opacity), "shs": f32(shs), "scales": f32(scales),
+            "rotations": f32(rotations)}
+
+
+def make_pixel_grads(cam: Camera, seed: int = SEED + 1, with_opacity: bool = False) -> dict[str, np.ndarray]:
+    """Upstream image gradients ~ N(0,1)/N_px; dL/dopacity is zero unless requested, like
+    the loss of /root/reference/src/core/mapper.py:381-438 which never touches the opacity image."""
+    rng = np.random.default_rng(seed)
+    H, W = cam.height, cam.width
+    n = float(H * W)
+    g = {
+        "color": rng.normal(size=(3, H, W)) / n,
+        "normal": rng.normal(size=(3, H, W)) / n,
+        "depth": rng.normal(size=(1, H, W)) / n,
+        "opacity": (rng.normal(size=(1, H, W)) / n) if with_opacity else np.zeros((1, H, W)),
+    }
+    return {k: np.ascontiguousarray(a, dtype=np.float32) for k, a in g.items()}
+
+
+CONFIGS = {
+    # name: (P, W, H, layers, sh_degree)   -- BASELINE.json configs / SURVEY 8 table
+    "C1": (10_000, 256, 256, 2, 3),
+    "C2": (600_000, 1200, 680, 4, 3),
+    "C3": (1_000_000, 1920, 1080, 4, 3),
+    "C4": (4_000_000, 1920, 1080, 4, 3),
+    "C5": (300_000, 640, 480, 4, 0),
+}
+
+
+def make_config(name: str, seed: int = SEED):
+    P, W, H, L, deg = CONFIGS[name]
+    cam = default_camera(W, H)
+    return cam, make_scene(P, cam, layers=L, sh_degree=deg, seed=seed)

@@ -1,0 +1,113 @@
+"""Generates tests/golden/*.npz with the UNMODIFIED reference rasterizer (oracle/_ref, built by
+oracle/build_ref.sh from /root/reference) on a CUDA GPU.  Run on the B200 box:
+
+    gpurun -- 'python tests/golden/make_golden.py gpurun_out/golden'
+
+then copy the .npz files into tests/golden/ and commit them.  Each file holds the seeded inputs' identity
+(config name, seed, camera pose id), the reference's images, gradients and every index artefact decoded from
+its geometry / binning / image workspaces.  The oracle and the CUDA path are both tested against these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from eggfusion_b200 import synthetic as syn  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+# name -> (P, W, H, layers, sh_degree, pose, with_opacity_grad, bg, tile_mask_kind)
+CASES = {
+    "c1_identity": (10_000, 256, 256, 2, 3, None, False, (0, 0, 0), "ones"),
+    "c1_posed_bg": (10_000, 256, 256, 2, 3, ((0.15, -0.1, 0.05), 0.12, -0.07), True, (0.2, 0.5, 0.7), "ones"),
+    "small_deg0_ragged": (3_000, 200, 136, 3, 0, ((-0.05, 0.08, -0.1), -0.1, 0.05), True, (0, 0, 0), "checker"),
+    "small_deg1": (2_000, 160, 96, 2, 1, None, False, (0, 0, 0), "ones"),
+    "small_deg2": (2_000, 160, 96, 2, 2, None, False, (0, 0, 0), "ones"),
+}
+
+
+def case_inputs(name):
+    P, W, H, L, deg, pose, with_op, bg, mask_kind = CASES[name]
+    base = syn.default_camera(W, H)
+    sc = syn.make_scene(P, base, layers=L, sh_degree=deg)
+    cam = base if pose is None else syn.default_camera(W, H, syn.look_from(*pose))
+    g = syn.make_pixel_grads(cam, with_opacity=with_op)
+    ty, tx = cam.tiles
+    mask = np.ones((ty, tx), np.int32)
+    if mask_kind == "checker":
+        mask[::2, 1::2] = 0
+        mask[1::2, ::2] = 0
+    return cam, sc, g, np.asarray(bg, np.float32), mask, deg
+
+
+def run_reference(name, device="cuda"):
+    ref = ref_loader.load()
+    cam, sc, g, bg, mask, deg = case_inputs(name)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    P = sc["xyz"].shape[0]
+    M = sc["shs"].shape[1]
+    settings = ref.GaussianRasterizationSettings(
+        image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=t(bg),
+        scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=deg,
+        campos=t(cam.campos), prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+    means, shs, opac, scales, rots = t(sc["xyz"]), t(sc["shs"]), t(sc["opacity"]), t(sc["scales"]), t(sc["rotations"])
+    empty = torch.Tensor([])
+    args = (settings.bg, means, empty, opac, scales, rots, settings.scale_modifier, empty, settings.viewmatrix,
+            settings.projmatrix, t(mask), settings.tanfovx, settings.tanfovy, settings.image_height,
+            settings.image_width, settings.cx, settings.cy, shs, settings.sh_degree, settings.campos, False, False)
+    (num_rendered, num_tile, color, normal, depth, opac_img, active, radii, geomB, binB, imgB,
+     tile_indices) = ref._C.rasterize_gaussians(*args)
+    torch.cuda.synchronize()
+    bargs = (tile_indices, num_tile, settings.bg, means, radii, empty, scales, rots, settings.scale_modifier, empty,
+             settings.viewmatrix, settings.projmatrix, settings.tanfovx, settings.tanfovy, t(g["color"]),
+             t(g["normal"]), t(g["depth"]), t(g["opacity"]), shs, settings.sh_degree, settings.campos, geomB,
+             num_rendered, binB, imgB, False)
+    (d_means2D, d_colors, d_opacity, d_means3D, d_cov3D, d_sh, d_scales, d_rots) = \
+        ref._C.rasterize_gaussians_backward(*bargs)
+    torch.cuda.synchronize()
+    geom = ref_loader.decode_geom(geomB, P)
+    img = ref_loader.decode_img(imgB, cam.width * cam.height)
+    binn = ref_loader.decode_binning(binB, num_rendered)
+    tiles = cam.tiles[0] * cam.tiles[1]
+    vis = radii.cpu().numpy() > 0
+    out = {
+        "num_rendered": np.int64(num_rendered), "tile_num": np.int64(num_tile),
+        "color": color.cpu().numpy(), "normal_img": normal.cpu().numpy(), "depth": depth.cpu().numpy(),
+        "opacity": opac_img.cpu().numpy(), "active_mask": active.cpu().numpy(), "radii": radii.cpu().numpy(),
+        "tile_indices": tile_indices.cpu().numpy()[:tiles].copy(),
+        "ranges": img["ranges"][:tiles].copy(), "n_contrib": img["n_contrib"].copy(),
+        "final_T": img["accum_alpha"].copy(), "final_D": img["accum_depth"].copy(),
+        "point_list": binn["point_list"].copy(), "point_list_keys": binn["point_list_keys"].copy(),
+        "tiles_touched": geom["tiles_touched"].copy(),
+        # per-surfel state is only defined for visible surfels (the reference leaves the rest uninitialised)
+        "vis_index": np.nonzero(vis)[0].astype(np.int32),
+        "means2D": geom["means2D"][vis], "depths": geom["depths"][vis], "cov3D": geom["cov3D"][vis],
+        "conic_opacity": geom["conic_opacity"][vis], "rgb": geom["rgb"][vis], "normal": geom["normal"][vis],
+        "Jinv": geom["Jinv"][vis], "clamped": geom["clamped"][vis],
+        "dL_dmeans2D": d_means2D.cpu().numpy(), "dL_dcolors": d_colors.cpu().numpy(),
+        "dL_dopacity": d_opacity.cpu().numpy(), "dL_dmeans3D": d_means3D.cpu().numpy(),
+        "dL_dcov3D": d_cov3D.cpu().numpy(), "dL_dsh": d_sh.cpu().numpy(), "dL_dscales": d_scales.cpu().numpy(),
+        "dL_drotations": d_rots.cpu().numpy(),
+    }
+    return out
+
+
+def main():
+    outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(outdir, exist_ok=True)
+    for name in CASES:
+        out = run_reference(name)
+        # second run: the float atomics of the reference backward are order-nondeterministic; record the spread
+        out2 = run_reference(name)
+        for k in ("dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations", "dL_dopacity"):
+            out["rerun_absdiff_" + k] = np.float64(np.abs(out[k] - out2[k]).max())
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
+        print(name, "I=%d tiles=%d vis=%d" % (out["num_rendered"], out["tile_num"], len(out["vis_index"])),
+              "size=%.2f MB" % (os.path.getsize(os.path.join(outdir, name + ".npz")) / 1e6))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,74 @@
+// hostemu.cpp -- TEST ONLY.  Compiles the product's __host__ __device__ per-surfel math
+// (eggfusion_b200/csrc/egs_surfel_math.cuh) for the CPU so that tests without a GPU can compare the exact
+// arithmetic the kernels run against the oracle.  Never loaded by the product path.
+#include "../../eggfusion_b200/csrc/egs_surfel_math.cuh"
+#include <cstring>
+
+static FrameConst make_fc(int W, int H, int D, int M, float tanfovx, float tanfovy, float cx, float cy, float mod,
+                          const float* view, const float* proj, const float* campos, const float* bg) {
+    FrameConst fc;
+    memcpy(fc.view, view, 64);
+    memcpy(fc.proj, proj, 64);
+    memcpy(fc.campos, campos, 12);
+    memcpy(fc.bg, bg, 12);
+    fc.tanfovx = tanfovx; fc.tanfovy = tanfovy;
+    fc.fy = H / (2.0f * tanfovy);
+    fc.fx = W / (2.0f * tanfovx);
+    fc.cx = cx; fc.cy = cy; fc.mod = mod;
+    fc.W = W; fc.H = H; fc.gx = (W + 15) / 16; fc.gy = (H + 15) / 16; fc.D = D; fc.M = M;
+    return fc;
+}
+
+extern "C" {
+
+void emu_surfel_forward(int P, int W, int H, int D, int M, float tanfovx, float tanfovy, float cx, float cy, float mod,
+                        const float* view, const float* proj, const float* campos, const float* bg, const float* means,
+                        const float* scales, const float* rots, const float* opac, const float* shs,
+                        const float* colors, int32_t* radii, uint8_t* active, float* records /*[P][16]*/,
+                        float* cov3D /*[P][6]*/, uint8_t* clamped /*[P]*/, int32_t* rect /*[P][4]*/) {
+    const FrameConst fc = make_fc(W, H, D, M, tanfovx, tanfovy, cx, cy, mod, view, proj, campos, bg);
+    for (int i = 0; i < P; i++) {
+        SurfelFwd o;
+        memset(&o, 0, sizeof(o));
+        const bool use_sh = colors == nullptr;
+        surfel_forward(fc, means + 3 * i, scales + 3 * i, rots + 4 * i, opac[i],
+                       use_sh ? shs + (size_t)3 * M * i : colors + 3 * i, use_sh, o);
+        radii[i] = o.radius;
+        active[i] = (uint8_t)o.active;
+        if (o.radius > 0) {
+            memcpy(records + 16 * (size_t)i, &o.rec, 64);
+            memcpy(cov3D + 6 * (size_t)i, o.cov3D, 24);
+            clamped[i] = (uint8_t)o.clamped;
+            rect[4 * i] = o.x0; rect[4 * i + 1] = o.y0; rect[4 * i + 2] = o.x1; rect[4 * i + 3] = o.y1;
+        }
+    }
+}
+
+void emu_surfel_backward(int P, int W, int H, int D, int M, float tanfovx, float tanfovy, float cx, float cy, float mod,
+                         const float* view, const float* proj, const float* campos, const float* bg, const float* means,
+                         const float* scales, const float* rots, const float* shs, const int32_t* radii,
+                         const float* cov3D, const uint8_t* clamped, const float* screen_grads /*[P][16]*/,
+                         float* d_means, float* d_sh, float* d_scales, float* d_rots, float* d_cov3D) {
+    const FrameConst fc = make_fc(W, H, D, M, tanfovx, tanfovy, cx, cy, mod, view, proj, campos, bg);
+    for (int i = 0; i < P; i++) {
+        if (!(radii[i] > 0)) continue;
+        SurfelBwd o;
+        const float* g16 = screen_grads + 16 * (size_t)i;
+        surfel_backward_geom(fc, means + 3 * i, scales + 3 * i, rots + 4 * i, cov3D + 6 * (size_t)i, g16, o);
+        if (shs) {
+            const float* mean = means + 3 * i;
+            const float dir[3] = {mean[0] - fc.campos[0], mean[1] - fc.campos[1], mean[2] - fc.campos[2]};
+            const float gcol[3] = {g16[6], g16[7], g16[8]};
+            float add[3];
+            float* my_sh = d_sh + (size_t)3 * M * i;
+            sh_backward(D, shs + (size_t)3 * M * i, dir, (uint32_t)clamped[i], gcol,
+                        [my_sh](int k, int ch, float v) { my_sh[3 * k + ch] = v; }, add);
+            o.d_mean[0] += add[0]; o.d_mean[1] += add[1]; o.d_mean[2] += add[2];
+        }
+        memcpy(d_means + 3 * (size_t)i, o.d_mean, 12);
+        memcpy(d_scales + 3 * (size_t)i, o.d_scale, 12);
+        memcpy(d_rots + 4 * (size_t)i, o.d_rot, 16);
+        memcpy(d_cov3D + 6 * (size_t)i, o.d_cov3D, 24);
+    }
+}
+}

@@ -1,0 +1,301 @@
+"""GPU parity tests: the sm_100a path (called through the C-ABI) against the CPU oracle, the committed golden
+vectors of the reference, and -- when oracle/_ref is present -- the compiled reference itself on the same inputs.
+
+Bar (BASELINE.json north_star): index artefacts bit-exact (radii, active mask, tiles touched, sorted point list,
+tile ranges, active-tile list); images and gradients within 1e-4 relative (tensor-wise max |a-b| / max |b|).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from util import bits, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # north_star tolerance, tensor-wise relative
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _settings(E, cam, bg, deg):
+    return E.GaussianRasterizationSettings(
+        image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=_t(bg),
+        scale_modifier=1.0, viewmatrix=_t(cam.viewmatrix), projmatrix=_t(cam.projmatrix), sh_degree=deg,
+        campos=_t(cam.campos), prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+
+
+def cuda_run(name, capacity=None):
+    """Forward + backward of one seeded case through forward_raw/backward_raw (thin wrappers over the C-ABI)."""
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R
+    cam, sc, g, bg, mask, deg = util.case_inputs(name)
+    s = _settings(E, cam, bg, deg)
+    P = sc["xyz"].shape[0]
+    empty = torch.Tensor([])
+    means, shs, opac = _t(sc["xyz"]), _t(sc["shs"]), _t(sc["opacity"])
+    scales, rots = _t(sc["scales"]), _t(sc["rotations"])
+    color, normal, depth, opacity, active, radii, st = R.forward_raw(s, means, shs, empty, opac, scales, rots,
+                                                                    _t(mask), capacity=capacity)
+    dbg = R.debug_export(st, P, cam.width, cam.height)
+    grads = R.backward_raw(st, means, shs, empty, scales, rots, _t(g["color"]), _t(g["normal"]), _t(g["depth"]),
+                           _t(g["opacity"]), want_aux=True)
+    torch.cuda.synchronize()
+    c = lambda t: None if t is None else t.cpu().numpy()
+    out = {"color": c(color), "normal_img": c(normal), "depth": c(depth), "opacity": c(opacity),
+           "active_mask": c(active), "radii": c(radii), "num_rendered": st.num_rendered, "tile_num": st.tile_num}
+    out.update({k: c(v) for k, v in dbg.items()})
+    out.update({"g_" + k: c(v) for k, v in grads.items()})
+    return out
+
+
+def _check_index_artefacts(out, ref_radii, ref_active, ref_tiles_touched, ref_point_list, ref_ranges,
+                           ref_tile_indices, ref_I, ref_tile_num):
+    assert np.array_equal(out["radii"], ref_radii)
+    assert np.array_equal(out["active_mask"].astype(np.uint8), np.asarray(ref_active).astype(np.uint8))
+    assert np.array_equal(out["tiles_touched"].astype(np.uint32), np.asarray(ref_tiles_touched).astype(np.uint32))
+    assert out["num_rendered"] == int(ref_I)
+    assert out["tile_num"] == int(ref_tile_num)
+    assert np.array_equal(out["point_list"].astype(np.uint32), np.asarray(ref_point_list).astype(np.uint32))
+    assert np.array_equal(out["ranges"].astype(np.uint32), np.asarray(ref_ranges).astype(np.uint32))
+    assert np.array_equal(out["tile_indices"], np.asarray(ref_tile_indices).astype(np.int32))
+
+
+def _check_images(out, color, normal, depth, opacity, n_contrib, final_T, tol=TOL):
+    assert rel_err(out["color"], color) <= tol
+    assert rel_err(out["normal_img"], normal) <= tol
+    assert rel_err(out["depth"], depth) <= tol
+    assert rel_err(out["opacity"], opacity) <= tol
+    # n_contrib is an index artefact that depends on exp() to the last ulp: identical except for isolated pixels
+    mism = np.mean(out["n_contrib"].astype(np.int64) != np.asarray(n_contrib).astype(np.int64))
+    assert mism <= 2e-4, mism
+    if final_T is not None:
+        assert rel_err(out["final_T"], final_T) <= tol
+
+
+GRAD_KEYS = [("g_means3D", "dL_dmeans3D"), ("g_sh", "dL_dsh"), ("g_scales", "dL_dscales"),
+             ("g_rotations", "dL_drotations"), ("g_opacities", "dL_dopacity"), ("g_means2D", "dL_dmean2D"),
+             ("g_colors", "dL_dcolors"), ("g_cov3D", "dL_dcov3D")]
+
+
+def _check_grads(out, ref, tol=TOL, keymap=None):
+    for mine, theirs in GRAD_KEYS:
+        tk = (keymap or {}).get(theirs, theirs)
+        if tk not in ref:
+            continue
+        a, b = out[mine], np.asarray(ref[tk])
+        assert a.shape == b.shape or a.size == b.size, (mine, a.shape, b.shape)
+        e = rel_err(a.reshape(-1), b.reshape(-1))
+        assert e <= tol, (mine, e)
+
+
+@pytest.mark.parametrize("name", util.case_names())
+def test_cuda_matches_oracle(name):
+    cam, sc, g, bg, mask, deg, f, b = util.oracle_run(name)
+    out = cuda_run(name)
+    _check_index_artefacts(out, f["radii"], f["active_mask"], f["tiles_touched"], f["point_list"], f["ranges"],
+                           f["tile_indices"], f["num_rendered"], f["tile_num"])
+    vis = f["radii"] > 0
+    rec = out["records"]
+    # index-critical per-surfel quantities are bit-exact against the oracle
+    assert np.array_equal(bits(rec[vis, 0:2]), bits(f["means2D"][vis]))
+    assert np.array_equal(bits(rec[vis, 7]), bits(f["depths"][vis]))
+    assert np.array_equal(bits(rec[vis][:, [4, 5, 6]]), bits(f["conic_opacity"][vis][:, :3]))
+    assert np.array_equal(bits(out["cov3D"][vis]), bits(f["cov3D"][vis]))
+    assert rel_err(rec[vis][:, [10, 11, 12]], f["rgb"][vis]) <= 1e-6
+    assert rel_err(rec[vis][:, 13:16], f["normal"][vis]) <= 1e-6
+    _check_images(out, f["color"], f["out_normal"], f["depth"], f["opacity"], f["n_contrib"], f["final_T"])
+    _check_grads(out, b)
+    sg = util.screen_block_from_oracle(b, sc["xyz"].shape[0])
+    assert rel_err(out["g_screen"], sg) <= TOL
+
+
+@pytest.mark.parametrize("name", util.case_names())
+def test_cuda_matches_reference_golden(name):
+    path = util.golden_path(name)
+    if not os.path.exists(path):
+        pytest.skip("golden file not generated yet")
+    G = np.load(path)
+    out = cuda_run(name)
+    _check_index_artefacts(out, G["radii"], G["active_mask"], G["tiles_touched"], G["point_list"], G["ranges"],
+                           G["tile_indices"], G["num_rendered"], G["tile_num"])
+    vis = G["vis_index"]
+    rec = out["records"][vis]
+    assert np.array_equal(bits(rec[:, 0:2]), bits(G["means2D"]))
+    assert np.array_equal(bits(rec[:, 7]), bits(G["depths"]))
+    assert np.array_equal(bits(rec[:, [4, 5, 6]]), bits(G["conic_opacity"][:, :3]))
+    assert np.array_equal(bits(out["cov3D"][vis]), bits(G["cov3D"]))
+    _check_images(out, G["color"], G["normal_img"], G["depth"], G["opacity"], G["n_contrib"], G["final_T"])
+    _check_grads(out, G, keymap={"dL_dmean2D": "dL_dmeans2D"})
+
+
+@pytest.mark.parametrize("name", ["c1_identity", "small_deg0_ragged"])
+def test_cuda_matches_live_reference(name):
+    """Same tensors through the compiled, unmodified reference on this GPU (only where oracle/_ref travelled)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(util.GOLDEN_DIR, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    G = mg.run_reference(name, DEV)
+    out = cuda_run(name)
+    _check_index_artefacts(out, G["radii"], G["active_mask"], G["tiles_touched"], G["point_list"], G["ranges"],
+                           G["tile_indices"], G["num_rendered"], G["tile_num"])
+    _check_images(out, G["color"], G["normal_img"], G["depth"], G["opacity"], G["n_contrib"], G["final_T"])
+    _check_grads(out, G, keymap={"dL_dmean2D": "dL_dmeans2D"})
+
+
+def test_dropin_autograd_api_matches_raw():
+    """The reference-facing call: GaussianRasterizer(...)(means3D=..., shs=..., ...) + loss.backward()."""
+    import eggfusion_b200 as E
+    name = "small_deg1"
+    cam, sc, g, bg, mask, deg = util.case_inputs(name)
+    raw = cuda_run(name)
+    s = _settings(E, cam, bg, deg)
+    leaf = {k: _t(sc[k]).requires_grad_(True) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
+    rast = E.GaussianRasterizer(raster_settings=s)
+    color, normal, depth, opac, active, radii = rast(
+        means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], colors_precomp=None, scales=leaf["scales"],
+        rotations=leaf["rotations"], cov3D_precomp=None, tile_mask=_t(mask))
+    loss = (color * _t(g["color"])).sum() + (normal * _t(g["normal"])).sum() + (depth * _t(g["depth"])).sum() + \
+           (opac * _t(g["opacity"])).sum()
+    loss.backward()
+    assert np.array_equal(color.detach().cpu().numpy(), raw["color"])
+    assert active.dtype == torch.bool and radii.dtype == torch.int32
+    for k, gk in (("xyz", "g_means3D"), ("opacity", "g_opacities"), ("shs", "g_sh"), ("scales", "g_scales"),
+                  ("rotations", "g_rotations")):
+        assert leaf[k].grad is not None and leaf[k].grad.shape == leaf[k].shape
+        assert rel_err(leaf[k].grad.cpu().numpy(), raw[gk]) <= 1e-5, k   # atomics order only
+
+
+def test_colors_precomp_path():
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R
+    from oracle import oracle as orc
+    name = "small_deg0_ragged"
+    cam, sc, g, bg, mask, deg = util.case_inputs(name)
+    rng = np.random.default_rng(5)
+    cols = rng.uniform(0, 1, size=(sc["xyz"].shape[0], 3)).astype(np.float32)
+    oc = orc.cam_from_synthetic(cam, 0, 0, bg=bg)
+    f = orc.forward(oc, sc["xyz"], sc["scales"], sc["rotations"], sc["opacity"], None, colors_precomp=cols,
+                    tile_mask=mask)
+    b = orc.backward(oc, f, sc["xyz"], sc["scales"], sc["rotations"], None, g["color"], g["normal"], g["depth"],
+                     g["opacity"], colors_precomp=cols)
+    s = _settings(E, cam, bg, 0)
+    empty = torch.Tensor([])
+    means, opac, scales, rots = _t(sc["xyz"]), _t(sc["opacity"]), _t(sc["scales"]), _t(sc["rotations"])
+    color, normal, depth, opacity, active, radii, st = R.forward_raw(s, means, empty, _t(cols), opac, scales, rots,
+                                                                    _t(mask))
+    gr = R.backward_raw(st, means, empty, _t(cols), scales, rots, _t(g["color"]), _t(g["normal"]), _t(g["depth"]),
+                        _t(g["opacity"]))
+    assert np.array_equal(radii.cpu().numpy(), f["radii"])
+    assert rel_err(color.cpu().numpy(), f["color"]) <= TOL
+    assert rel_err(gr["colors_precomp"].cpu().numpy(), b["dL_dcolors"]) <= TOL
+    assert rel_err(gr["means3D"].cpu().numpy(), b["dL_dmeans3D"]) <= TOL
+    assert gr["sh"] is None
+
+
+def test_empty_and_fully_culled_inputs():
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R
+    cam, sc, g, bg, mask, deg = util.case_inputs("small_deg1")
+    s = _settings(E, cam, bg, deg)
+    empty = torch.Tensor([])
+    z = lambda *shape: torch.zeros(*shape, device=DEV)
+    # P == 0: images of zeros, num_rendered 0 (rasterize_points.cu:89-131)
+    color, normal, depth, opacity, active, radii, st = R.forward_raw(s, z(0, 3), z(0, 4, 3), empty, z(0, 1), z(0, 3),
+                                                                    z(0, 4), None)
+    assert st.num_rendered == 0 and st.tile_num == 0
+    for img in (color, normal, depth, opacity):
+        assert float(img.abs().max()) == 0.0
+    # every surfel behind the camera
+    means = _t(sc["xyz"]).clone()
+    means[:, 2] = -means[:, 2]
+    out = R.forward_raw(s, means, _t(sc["shs"]), empty, _t(sc["opacity"]), _t(sc["scales"]), _t(sc["rotations"]), None)
+    assert out[6].num_rendered == 0
+    assert int(out[5].abs().max()) == 0 and not bool(out[4].any())
+    assert float(out[0].abs().max()) == 0.0
+    gr = R.backward_raw(out[6], means, _t(sc["shs"]), empty, _t(sc["scales"]), _t(sc["rotations"]), _t(g["color"]),
+                        _t(g["normal"]), _t(g["depth"]), _t(g["opacity"]))
+    for k in ("means3D", "sh", "scales", "rotations", "opacities"):
+        assert float(gr[k].abs().max()) == 0.0
+
+
+def test_fixed_capacity_mode_and_overflow_detection():
+    from eggfusion_b200 import rasterizer as R
+    name = "small_deg2"
+    exact = cuda_run(name)
+    roomy = cuda_run(name, capacity=exact["num_rendered"] + 1000)
+    assert np.array_equal(roomy["color"], exact["color"])
+    assert np.array_equal(roomy["point_list"][:exact["num_rendered"]], exact["point_list"])
+    R._check_pending(block=True)
+    cuda_run(name, capacity=max(1, exact["num_rendered"] // 2))
+    with pytest.raises(RuntimeError, match="truncated"):
+        R._check_pending(block=True)
+
+
+def test_mark_visible_matches_oracle():
+    import eggfusion_b200 as E
+    from oracle import oracle as orc
+    cam, sc, g, bg, mask, deg = util.case_inputs("c1_posed_bg")
+    s = _settings(E, cam, bg, deg)
+    rng = np.random.default_rng(3)
+    pts = (sc["xyz"] * rng.uniform(0.05, 2.0, size=(sc["xyz"].shape[0], 1))).astype(np.float32)
+    got = E.GaussianRasterizer(s).markVisible(_t(pts)).cpu().numpy()
+    want = orc.mark_visible(pts, cam.viewmatrix, cam.projmatrix)
+    assert np.array_equal(got, want)
+
+
+def test_properties_at_full_size():
+    """Size-independent properties at BASELINE's headline size (1M surfels, 1920x1080), where the oracle would
+    take minutes: list sortedness, range consistency, tile-mask linearity of images and gradients."""
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R, synthetic as syn, parallel as par
+    cam, sc = syn.make_config("C3")
+    g = syn.make_pixel_grads(cam)
+    bg = np.zeros(3, np.float32)
+    s = _settings(E, cam, bg, 3)
+    empty = torch.Tensor([])
+    P = sc["xyz"].shape[0]
+    means, shs, opac = _t(sc["xyz"]), _t(sc["shs"]), _t(sc["opacity"])
+    scales, rots = _t(sc["scales"]), _t(sc["rotations"])
+    gt = [_t(g[k]) for k in ("color", "normal", "depth", "opacity")]
+    color, normal, depth, opacity, active, radii, st = R.forward_raw(s, means, shs, empty, opac, scales, rots, None)
+    dbg = R.debug_export(st, P, cam.width, cam.height)
+    full = R.backward_raw(st, means, shs, empty, scales, rots, *gt)
+    I = st.num_rendered
+    assert I == int(dbg["tiles_touched"].sum())
+    assert int((radii > 0).sum()) > 0.8 * P
+    # per-tile lists: sorted by (depth bits, id); ranges tile the list exactly
+    pl = dbg["point_list"].long()
+    rec_depth = dbg["records"][:, 7].contiguous().view(torch.int32).long()
+    key = (rec_depth[pl] << 32) | pl
+    ranges = dbg["ranges"].long()
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == I
+    tile_of = torch.repeat_interleave(torch.arange(ranges.shape[0], device=DEV), lens)
+    same_tile = tile_of[1:] == tile_of[:-1]
+    assert bool(((key[1:] > key[:-1]) | ~same_tile).all())
+    nz = ranges[lens > 0]
+    assert bool((nz[1:, 0] == nz[:-1, 1]).all()) and int(nz[0, 0]) == 0 and int(nz[-1, 1]) == I
+    assert int((dbg["tile_indices"] >= 0).sum()) == st.tile_num == int((lens > 0).sum())
+    assert bool(torch.isfinite(color).all()) and bool(torch.isfinite(depth).all())
+    # linearity in the tile mask: two disjoint shards reproduce the frame and sum to its gradients
+    ty, tx = cam.tiles
+    acc = None
+    img_sum = torch.zeros_like(color)
+    for r in range(2):
+        m = par.tile_partition(ty, tx, 2, r).to(DEV)
+        c2, n2, d2, o2, a2, r2, st2 = R.forward_raw(s, means, shs, empty, opac, scales, rots, m)
+        img_sum += c2
+        g2 = R.backward_raw(st2, means, shs, empty, scales, rots, *gt)
+        acc = g2["screen"].clone() if acc is None else acc + g2["screen"]
+    assert torch.equal(img_sum, color)
+    assert rel_err(acc.cpu().numpy(), full["screen"].cpu().numpy()) <= 1e-5
