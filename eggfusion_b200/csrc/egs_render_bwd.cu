@@ -1,16 +1,23 @@
 // egs_render_bwd.cu -- reverse compositing walk: per-pixel gradients -> per-surfel screen-space gradients.
 //
 // Replaces renderCUDA<3> backward (DGS/cuda_rasterizer/backward.cu:419-676), which issues 13 float atomicAdds
-// per contributing (pixel, surfel) pair.  Here:
-//   * a warp owns an 8x4 pixel block and skips a splat whose alpha >= 1/255 ellipse cannot reach the block;
-//   * the 13 partials of the 32 pixels of a warp are summed with a transposing butterfly (16 shuffles; after it
-//     lane 2v holds the warp total of value v) instead of 13 x 5 shuffle-reduces;
-//   * the (at most 8) warp totals of a splat are combined through shared memory and leave the CTA as four
-//     16-byte vector reductions (red.global.add.v4.f32) into the [P][16] screen-gradient block: <= 4 vector
-//     atomics per (tile, surfel) instead of 13 scalar atomics per (pixel, surfel);
+// per contributing (pixel, surfel) pair.  This kernel is bound by instruction issue, not by HBM (ncu: DRAM < 2 %),
+// so the design minimises warp-instructions per (tile, surfel):
+//   * a warp owns an 8x4 pixel block.  While a batch of splat records is staged into shared memory, the staging
+//     thread of each record computes which of the 8 blocks its alpha >= 1/255 ellipse box can reach (one byte);
+//     a warp then walks only its own hits (ballot over the mask bytes + find-first-set), front of the list last;
+//   * the reference's 14 running accumulators (accum_rec / last_* for 3 colour, 3 normal, 1 depth channels) are
+//     folded into ONE scalar per pixel.  With kappa_j = sum_ch feature_ch(j) * dL/dpixel_ch and
+//     sigma_j = sum_{k behind j} w_k kappa_k, the reference's
+//         dL/dalpha_j = T_j * sum_ch (c_ch - accum_ch) g_ch + [normalisation, opacity, background terms]
+//     equals  T_j * kappa_j + (K0 - sigma_j) / (1 - alpha_j)  with a per-pixel constant K0 (same real-number value,
+//     different rounding order; parity is checked at 1e-4 relative);
+//   * the 13 partials of the 32 pixels of a warp are summed with a transposing butterfly (16 shuffles; lane 2v
+//     ends up with the warp total of value v), warp totals are combined through shared memory, and each
+//     (tile, surfel) leaves the CTA as four 16-byte vector reductions (red.global.add.v4.f32) into G[P][16];
 //   * the walk starts at the CTA-wide maximum of n_contrib, skipping list tails nobody blended.
-// The per-pair arithmetic follows the reference, including its deviations from the exact derivative:
-// x10 on the per-surfel normal gradient, the un-weighted depth-differencing term on mean2D (SURVEY 8 a-bis).
+// Reference quirks kept: x10 on the per-surfel normal gradient only, un-weighted depth-differencing term on
+// mean2D, conic.xy gradient not doubled (SURVEY 8 a-bis).
 #include "egs_common.cuh"
 
 #define BWD_BATCH 64
@@ -20,6 +27,12 @@ __device__ __forceinline__ float conic_power_b(float cxx, float cxy, float cyy, 
     const float q = __fmaf_rn(__fmul_rn(cxx, dx), dx, __fmul_rn(__fmul_rn(cyy, dy), dy));
     const float dist = __fmaf_rn(__fmul_rn(__fmul_rn(2.f, cxy), dx), dy, q);
     return __fmul_rn(-0.5f, dist);
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -65,12 +78,25 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
     v[0] += __shfl_xor_sync(full, v[0], 1);
 }
 
-__global__ void __launch_bounds__(EGS_TILE_THREADS)
+// Which of the tile's 8 warp blocks (2 columns x 4 rows of 8x4 pixels) can the record's extent box reach?
+__device__ __forceinline__ uint32_t block_mask(float x, float y, uint32_t ext, float tile_x0, float tile_y0) {
+    const float hx = (float)(ext & 0xffffu) * 0.125f + 3.5f, hy = (float)(ext >> 16) * 0.125f + 1.5f;
+    const float rx = x - tile_x0, ry = y - tile_y0;
+    const uint32_t xm = (fabsf(rx - 3.5f) <= hx ? 1u : 0u) | (fabsf(rx - 11.5f) <= hx ? 2u : 0u);
+    uint32_t m = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (fabsf(ry - (1.5f + 4.f * r)) <= hy) m |= xm << (2 * r);
+    return m;
+}
+
+__global__ void __launch_bounds__(EGS_TILE_THREADS, 3)
 k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
                   BinView bn, long long cap, const float* __restrict__ gC, const float* __restrict__ gN,
                   const float* __restrict__ gDp, const float* __restrict__ gOp, float* __restrict__ sg) {
     __shared__ float4 s_rec[BWD_BATCH * 4];
     __shared__ uint32_t s_id[BWD_BATCH];
+    __shared__ uint32_t s_wm[BWD_BATCH];
     __shared__ __align__(16) float s_part[BWD_WARPS][BWD_BATCH][16];
     __shared__ unsigned long long s_mask[BWD_WARPS];
     __shared__ int s_top;
@@ -91,7 +117,7 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
     const size_t pix = (size_t)W * py + px;
     const uint32_t* __restrict__ plist = bn.point_list + start;
     const float pxf = (float)px, pyf = (float)py;
-    const float bcx = (float)bx + 3.5f, bcy = (float)by + 1.5f;
+    const float tile_x0 = (float)(tx * EGS_TILE), tile_y0 = (float)(ty * EGS_TILE);
 
     if (threadIdx.x == 0) s_top = 0;
     __syncthreads();
@@ -108,26 +134,24 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
         gD = __ldg(gDp + pix);
         gO = __ldg(gOp + pix);
     }
-    {
-        int wmax = last_contributor;
+    int warp_last = last_contributor;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
-        if (lane == 0 && wmax > 0) atomicMax(&s_top, wmax);
-    }
+    for (int d = 16; d > 0; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, d));
+    if (lane == 0 && warp_last > 0) atomicMax(&s_top, warp_last);
     __syncthreads();
     const int top0 = s_top;
 
-    // per-pixel constants of the depth term (backward.cu:620-621), same evaluation order as the reference
+    // per-pixel constants.  backward.cu:620-621: the depth image is D / (1 - T_final)
     const float one_m_Tf = 1.f - T_final;
     const float gDn = gD / one_m_Tf;
-    const float kdepth = gD * D_final / one_m_Tf / one_m_Tf * -T_final;
     const float bg_dot = __ldg(bg) * gc0 + __ldg(bg + 1) * gc1 + __ldg(bg + 2) * gc2;
-    const float ddelx = 0.5f * (float)W, ddely = 0.5f * (float)H;
+    // K0 = [normalisation of depth] + [opacity image] - [background]   (backward.cu:621, :631, :638-641)
+    const float K0 = gD * D_final / one_m_Tf / one_m_Tf * -T_final + T_final * (gO - bg_dot);
+    const float kx = 2.f * 0.5f * (float)W, ky = 2.f * 0.5f * (float)H; // 2 * ddelx, 2 * ddely
+    const float gn0x = gn0 * 10.f, gn1x = gn1 * 10.f, gn2x = gn2 * 10.f;   // backward.cu:604
 
     float T = T_final;
-    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f, acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f, acc_d = 0.f;
-    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f, last_n0 = 0.f, last_n1 = 0.f, last_n2 = 0.f,
-          last_d = 0.f;
+    float sigma = 0.f;
 
     for (int top = top0; top > 0; top -= BWD_BATCH) {
         const int m = min(BWD_BATCH, top);
@@ -139,68 +163,63 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
             s_rec[threadIdx.x * 4] = a; s_rec[threadIdx.x * 4 + 1] = b;
             s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
+            s_wm[threadIdx.x] = block_mask(a.x, a.y, __float_as_uint(a.z), tile_x0, tile_y0);
+        } else if (threadIdx.x < BWD_BATCH) {
+            s_wm[threadIdx.x] = 0u;
         }
         __syncthreads();
 
         unsigned long long wmask = 0ull;
-        for (int j = 0; j < m; j++) {
-            const int pos = top - 1 - j; // index in the tile list == the reference's `contributor`
-            const float4 q0 = s_rec[4 * j];
-            const uint32_t ext = __float_as_uint(q0.z);
-            const float hx = (float)(ext & 0xffffu) * 0.125f, hy = (float)(ext >> 16) * 0.125f;
-            if (fabsf(q0.x - bcx) > hx + 3.5f || fabsf(q0.y - bcy) > hy + 1.5f) continue; // warp-uniform
-            const float4 q1 = s_rec[4 * j + 1];
-            const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
-            const float power = conic_power_b(q1.x, q1.y, q1.z, dx, dy);
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, __fmul_rn(q0.w, G));
-            const bool act = pos < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!__any_sync(0xffffffffu, act)) continue;
-
-            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = 0.f;
-            if (act) {
-                const float4 q2 = s_rec[4 * j + 2], q3 = s_rec[4 * j + 3];
-                const float one_m_a = 1.f - alpha;
-                T = T / one_m_a;
-                const float w = alpha * T;
-                const float ra = 1.f / one_m_a;
-                float dL_dalpha;
-                {   // colour (backward.cu:577-591)
-                    const float one_m_la = 1.f - last_alpha;
-                    acc_c0 = last_alpha * last_c0 + one_m_la * acc_c0; last_c0 = q2.z;
-                    acc_c1 = last_alpha * last_c1 + one_m_la * acc_c1; last_c1 = q2.w;
-                    acc_c2 = last_alpha * last_c2 + one_m_la * acc_c2; last_c2 = q3.x;
-                    dL_dalpha = (q2.z - acc_c0) * gc0 + (q2.w - acc_c1) * gc1 + (q3.x - acc_c2) * gc2;
-                    v[6] = w * gc0; v[7] = w * gc1; v[8] = w * gc2;
-                    // normal (backward.cu:593-606): x10 on the per-surfel gradient only
-                    acc_n0 = last_alpha * last_n0 + one_m_la * acc_n0; last_n0 = q3.y;
-                    acc_n1 = last_alpha * last_n1 + one_m_la * acc_n1; last_n1 = q3.z;
-                    acc_n2 = last_alpha * last_n2 + one_m_la * acc_n2; last_n2 = q3.w;
-                    dL_dalpha += (q3.y - acc_n0) * gn0 + (q3.z - acc_n1) * gn1 + (q3.w - acc_n2) * gn2;
-                    v[9] = w * gn0 * 10.f; v[10] = w * gn1 * 10.f; v[11] = w * gn2 * 10.f;
-                    // plane-corrected depth (backward.cu:609-627)
+        for (int c = 0; c < BWD_BATCH / 32; c++) {
+            // entry j of the batch is list position top-1-j (back to front); skip what nobody in this warp blended
+            const int jl = c * 32 + lane;
+            const bool mine = (s_wm[jl] >> warp & 1u) && (top - 1 - jl) < warp_last;
+            unsigned hits = __ballot_sync(0xffffffffu, mine);
+            while (hits) {
+                const int j = c * 32 + __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int pos = top - 1 - j; // index in the tile list == the reference's `contributor`
+                const float4 q0 = s_rec[4 * j];
+                const float4 q1 = s_rec[4 * j + 1];
+                const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
+                const float power = conic_power_b(q1.x, q1.y, q1.z, dx, dy);
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, __fmul_rn(q0.w, G));
+                const bool act = pos < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                if (!__any_sync(0xffffffffu, act)) continue;
+
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = 0.f;
+                if (act) {
+                    const float4 q2 = s_rec[4 * j + 2], q3 = s_rec[4 * j + 3];
+                    const float ra = rcp_approx(1.f - alpha);
+                    T = T * ra;                       // transmittance in front of this splat
+                    const float w = alpha * T;
                     const float d_cur = q1.w - (dx * q2.x + dy * q2.y);
-                    acc_d = last_alpha * last_d + one_m_la * acc_d; last_d = d_cur;
-                    dL_dalpha += kdepth * ra / T + (d_cur - acc_d) * gDn;
+                    // kappa = <features of this splat at this pixel, pixel gradients>
+                    float kappa = q2.z * gc0;
+                    kappa = fmaf(q2.w, gc1, kappa); kappa = fmaf(q3.x, gc2, kappa);
+                    kappa = fmaf(q3.y, gn0, kappa); kappa = fmaf(q3.z, gn1, kappa); kappa = fmaf(q3.w, gn2, kappa);
+                    kappa = fmaf(d_cur, gDn, kappa);
+                    const float dL_dalpha = fmaf(T, kappa, ra * (K0 - sigma));
+                    sigma = fmaf(w, kappa, sigma);
+                    const float dL_ddist = dL_dalpha * (q0.w * -0.5f * G);
+                    v[0] = fmaf(dL_ddist * kx, q1.x * dx + q1.y * dy, -gD * q2.x);   // backward.cu:648-660
+                    v[1] = fmaf(dL_ddist * ky, q1.z * dy + q1.y * dx, -gD * q2.y);
+                    v[2] = dL_ddist * dx * dx;
+                    v[3] = dL_ddist * dx * dy;
+                    v[4] = dL_ddist * dy * dy;
+                    v[5] = G * dL_dalpha;
+                    v[6] = w * gc0; v[7] = w * gc1; v[8] = w * gc2;
+                    v[9] = w * gn0x; v[10] = w * gn1x; v[11] = w * gn2x;
                     v[12] = w * gDn;
                 }
-                dL_dalpha *= T;
-                dL_dalpha += gO * T_final * ra;       // opacity image (backward.cu:631)
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * ra) * bg_dot; // background (backward.cu:638-641)
-                const float dL_ddist = dL_dalpha * q0.w * -0.5f * G;
-                v[0] = dL_ddist * 2.f * (q1.x * dx + q1.y * dy) * ddelx - gD * q2.x; // backward.cu:648-660
-                v[1] = dL_ddist * 2.f * (q1.z * dy + q1.y * dx) * ddely - gD * q2.y;
-                v[2] = dL_ddist * (dx * dx);
-                v[3] = dL_ddist * (dx * dy);
-                v[4] = dL_ddist * (dy * dy);
-                v[5] = G * dL_dalpha;
+                warp_transpose_reduce16(v, lane);
+                if (!(lane & 1)) s_part[warp][j][lane >> 1] = v[0];
+                wmask |= 1ull << j;
             }
-            warp_transpose_reduce16(v, lane);
-            if (!(lane & 1)) s_part[warp][j][lane >> 1] = v[0];
-            wmask |= 1ull << j;
         }
         if (lane == 0) s_mask[warp] = wmask;
         __syncthreads();

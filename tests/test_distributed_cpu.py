@@ -1,0 +1,93 @@
+"""Host-side logic of the multi-GPU sharding (eggfusion_b200/parallel.py) on CPU: tile partition, surfel ranges,
+and the one collective (reduce-scatter of the screen-gradient block) with world_size 2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from eggfusion_b200 import parallel as par
+
+
+def test_tile_partition_is_a_partition():
+    for world in (1, 2, 3, 4, 8):
+        ty, tx = 68, 120
+        masks = [par.tile_partition(ty, tx, world, r) for r in range(world)]
+        total = torch.stack(masks).sum(0)
+        assert torch.equal(total, torch.ones_like(total))
+        assert all(m.dtype == torch.int32 for m in masks)
+
+
+def test_cost_balanced_partition():
+    ty, tx, world = 40, 30, 4
+    rng = np.random.default_rng(0)
+    costs = torch.from_numpy(rng.pareto(1.5, size=(ty, tx)) * 100)
+    masks = [par.tile_partition(ty, tx, world, r, costs) for r in range(world)]
+    assert torch.equal(torch.stack(masks).sum(0), torch.ones((ty, tx), dtype=torch.int32))
+    loads = torch.tensor([float((costs * m).sum()) for m in masks])
+    naive = torch.tensor([float((costs * par.tile_partition(ty, tx, world, r)).sum()) for r in range(world)])
+    assert loads.max() <= naive.max() + 1e-9
+    assert loads.max() / loads.mean() < 1.25
+
+
+def test_surfel_ranges_cover_exactly():
+    for P in (0, 1, 7, 1000, 1_000_003):
+        for world in (1, 2, 4, 8):
+            rows = par.padded_rows(P, world)
+            assert rows % world == 0 and rows >= P and rows - P < world
+            spans = [par.surfel_range(P, world, r) for r in range(world)]
+            covered = 0
+            for first, count in spans:
+                assert first == min(P, covered) or count == 0
+                covered += count
+            assert covered == P
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, P, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows = par.padded_rows(P, world)
+        g = torch.Generator().manual_seed(100 + rank)
+        block = torch.zeros((rows, 16))
+        block[:P] = torch.randn((P, 16), generator=g)
+        mine = par.reduce_scatter_rows(block, None)
+        first, count = par.surfel_range(P, world, rank)
+        out[rank] = (first, count, mine.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [10, 1001])
+def test_reduce_scatter_rows_gloo_world2(P):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, P, out), nprocs=world, join=True)
+    rows = par.padded_rows(P, world)
+    full = torch.zeros((rows, 16))
+    for r in range(world):
+        g = torch.Generator().manual_seed(100 + r)
+        full[:P] += torch.randn((P, 16), generator=g)
+    chunk = rows // world
+    covered = 0
+    for r in range(world):
+        first, count, mine = out[r]
+        assert mine.shape == (chunk, 16)
+        assert torch.allclose(mine, full[r * chunk:(r + 1) * chunk], atol=1e-6)
+        assert first == r * chunk or count == 0
+        covered += count
+    assert covered == P

@@ -66,16 +66,30 @@ def _check_index_artefacts(out, ref_radii, ref_active, ref_tiles_touched, ref_po
     assert np.array_equal(out["tile_indices"], np.asarray(ref_tile_indices).astype(np.int32))
 
 
+def _active_pixels(tile_indices, tile_num, W, H):
+    """Pixels of tiles that own instances: the only place the reference defines its per-pixel saved state (its
+    image workspace is uninitialised elsewhere)."""
+    gx = (W + 15) // 16
+    act = np.zeros((H, W), bool)
+    for t in np.asarray(tile_indices)[:int(tile_num)]:
+        ty, tx = divmod(int(t), gx)
+        act[ty * 16:ty * 16 + 16, tx * 16:tx * 16 + 16] = True
+    return act.reshape(-1)
+
+
 def _check_images(out, color, normal, depth, opacity, n_contrib, final_T, tol=TOL):
     assert rel_err(out["color"], color) <= tol
     assert rel_err(out["normal_img"], normal) <= tol
     assert rel_err(out["depth"], depth) <= tol
     assert rel_err(out["opacity"], opacity) <= tol
+    H, W = out["depth"].shape[-2:]
+    act = _active_pixels(out["tile_indices"], out["tile_num"], W, H)
     # n_contrib is an index artefact that depends on exp() to the last ulp: identical except for isolated pixels
-    mism = np.mean(out["n_contrib"].astype(np.int64) != np.asarray(n_contrib).astype(np.int64))
+    mism = np.mean(out["n_contrib"][act].astype(np.int64) != np.asarray(n_contrib)[act].astype(np.int64))
     assert mism <= 2e-4, mism
+    assert int(np.abs(out["n_contrib"][~act]).max(initial=0)) == 0   # our workspace is zero where nothing was composited
     if final_T is not None:
-        assert rel_err(out["final_T"], final_T) <= tol
+        assert rel_err(out["final_T"][act], np.asarray(final_T)[act]) <= tol
 
 
 GRAD_KEYS = [("g_means3D", "dL_dmeans3D"), ("g_sh", "dL_dsh"), ("g_scales", "dL_dscales"),
