@@ -344,7 +344,7 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes": dom_bytes, "kernel_ms": stage_ms[dom_stage]},
         "clocks": clocks,
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": 7 * args.steps * world,
         "e2e": e2e,
     }
     if world == 1 and not args.no_cpu:
