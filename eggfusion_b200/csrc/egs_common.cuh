@@ -150,6 +150,19 @@ EGS_HD void egs_tile_rect(float px, float py, int radius, int gx, int gy, int& x
 }
 
 #if defined(__CUDACC__)
+// 16-byte shared-memory load from a 32-bit shared-window address.  Indexing __shared__ arrays through generic
+// pointers inside the hit loops made ptxas rebuild the window base (S2UR SR_CgaCtaId + UMOV + ULEA) per iteration.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a)); // opaque: keep it in a register instead of rematerialising the window base
+    return a;
+}
+
 // Stage the per-frame constants into shared memory (one pass, first 64 threads).
 __device__ __forceinline__ void load_frame_const(FrameConst& fc, const egs_frame& f) {
     const int t = threadIdx.x;

@@ -1,11 +1,11 @@
 // egs_preprocess.cu -- per-surfel kernels: forward projection (+ per-tile instance counting), per-surfel backward,
-// and the coarse visibility test.  One thread per surfel, 256-thread CTAs, per-frame constants staged in smem.
+// and the coarse visibility test.  One thread per surfel, 128-thread CTAs (the SH blocks live in registers), per-frame constants staged in smem.
 //
 // Replaces preprocessCUDA<3> (DGS/cuda_rasterizer/forward.cu:158-301), computeCov2DCUDA + preprocessCUDA<3> (bwd)
 // (DGS/cuda_rasterizer/backward.cu:144-416) and checkFrustum (DGS/cuda_rasterizer/rasterizer_impl.cu:54-66).
 #include "egs_surfel_math.cuh"
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
                  const float* __restrict__ colors, const int32_t* __restrict__ tile_mask, GeomView g, ImgView im,
@@ -19,14 +19,35 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
     if (valid) {
         SurfelFwd o;
         const bool use_sh = colors == nullptr;
-        const float* csrc = use_sh ? shs + (size_t)3 * fc.M * i : colors + (size_t)3 * i;
-        surfel_forward(fc, means + (size_t)3 * i, scales + (size_t)3 * i, rots + (size_t)4 * i, __ldg(opac + i), csrc,
-                       use_sh, o);
+        const float* mean = means + (size_t)3 * i;
+        surfel_forward(fc, mean, scales + (size_t)3 * i, rots + (size_t)4 * i, __ldg(opac + i), o);
         radii[i] = o.radius;
         active[i] = (uint8_t)o.active;
         uint32_t cnt = 0;
         if (o.radius > 0) {
             visible = true;
+            if (use_sh) {
+                // this surfel's SH block: 3*(D+1)^2 floats, fetched as 16-byte vectors when the rows allow it
+                // (the scalar pattern costs 32 L1 wavefronts per 4 bytes: it made this kernel L1-bound)
+                float shreg[48];
+                const float* src = shs + (size_t)3 * fc.M * i;
+                const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
+                if (((3 * fc.M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 12; q++)
+                        if (4 * q < nfl) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+                            shreg[4 * q] = v.x; shreg[4 * q + 1] = v.y; shreg[4 * q + 2] = v.z; shreg[4 * q + 3] = v.w;
+                        }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 48; k++)
+                        if (k < nfl) shreg[k] = __ldg(src + k);
+                }
+                surfel_color(fc, mean, shreg, true, o);
+            } else {
+                surfel_color(fc, mean, colors + (size_t)3 * i, false, o);
+            }
             float4* dst = reinterpret_cast<float4*>(g.rec + i);
             const float4* src = reinterpret_cast<const float4*>(&o.rec);
             dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -52,7 +73,7 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_surfel_backward(const egs_frame f, int first, int count, const float* __restrict__ means,
                   const float* __restrict__ shs, const float* __restrict__ colors, const float* __restrict__ scales,
                   const float* __restrict__ rots, const int32_t* __restrict__ radii, GeomView g,
@@ -84,10 +105,39 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
             const float dir[3] = {mean[0] - fc.campos[0], mean[1] - fc.campos[1], mean[2] - fc.campos[2]};
             const float gcol[3] = {g16[6], g16[7], g16[8]};
             float add[3];
-            const int used = (fc.D + 1) * (fc.D + 1);
-            sh_backward(fc.D, shs + (size_t)3 * M * i, dir, (uint32_t)g.clamped[i], gcol,
-                        [my_sh](int kk, int ch, float v) { my_sh[3 * kk + ch] = v; }, add);
-            for (int kk = 3 * used; kk < 3 * M; kk++) my_sh[kk] = 0.f; // coefficients above the active degree
+            const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
+            const bool vec = ((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                             (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0;
+            float shreg[48], dsh[48];
+            const float* src = shs + (size_t)3 * M * i;
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < 12; q++)
+                    if (4 * q < nfl) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+                        shreg[4 * q] = v.x; shreg[4 * q + 1] = v.y; shreg[4 * q + 2] = v.z; shreg[4 * q + 3] = v.w;
+                    }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 48; kk++)
+                    if (kk < nfl) shreg[kk] = __ldg(src + kk);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 48; kk++) dsh[kk] = 0.f;
+            sh_backward(fc.D, shreg, dir, (uint32_t)g.clamped[i], gcol,
+                        [&dsh](int kk, int ch, float v) { dsh[3 * kk + ch] = v; }, add);
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < 12; q++)
+                    if (4 * q < 3 * M)
+                        reinterpret_cast<float4*>(my_sh)[q] = make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]);
+                for (int kk = 48; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 48; kk++)
+                    if (kk < 3 * M) my_sh[kk] = dsh[kk];
+                for (int kk = 48; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+            }
             o.d_mean[0] += add[0]; o.d_mean[1] += add[1]; o.d_mean[2] += add[2];
         }
     } else {
@@ -99,8 +149,13 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
         for (int q = 0; q < 4; q++) o.d_rot[q] = 0.f;
 #pragma unroll
         for (int q = 0; q < 6; q++) o.d_cov3D[q] = 0.f;
-        if (use_sh)
-            for (int kk = 0; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+        if (use_sh) {
+            if (((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0) {
+                for (int q = 0; 4 * q < 3 * M; q++) reinterpret_cast<float4*>(my_sh)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int kk = 0; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+            }
+        }
     }
     d_means[3 * (size_t)i] = o.d_mean[0]; d_means[3 * (size_t)i + 1] = o.d_mean[1]; d_means[3 * (size_t)i + 2] = o.d_mean[2];
     d_scales[3 * (size_t)i] = o.d_scale[0]; d_scales[3 * (size_t)i + 1] = o.d_scale[1]; d_scales[3 * (size_t)i + 2] = o.d_scale[2];
@@ -139,7 +194,7 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
                                   GeomView g, ImgView im, int32_t* radii, uint8_t* active, cudaStream_t s) {
     const int P = f.num_surfels;
     if (P == 0) return cudaSuccess;
-    k_surfel_forward<<<(P + 255) / 256, 256, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im, radii,
+    k_surfel_forward<<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im, radii,
                                                      active);
     return cudaGetLastError();
 }
@@ -150,7 +205,7 @@ cudaError_t launch_surfel_backward(const egs_frame& f, int first, int count, con
                                    float* d_scales, float* d_rots, float* d_means2D, float* d_colors, float* d_cov3D,
                                    cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    k_surfel_backward<<<(count + 255) / 256, 256, 0, s>>>(f, first, count, means, shs, colors, scales, rots, radii, g,
+    k_surfel_backward<<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots, radii, g,
                                                           sg, d_means, d_opacity, d_sh, d_scales, d_rots, d_means2D,
                                                           d_colors, d_cov3D);
     return cudaGetLastError();

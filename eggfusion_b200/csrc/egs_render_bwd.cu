@@ -152,6 +152,7 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
 
     float T = T_final;
     float sigma = 0.f;
+    const uint32_t rec_base = smem_addr(s_rec);
 
     for (int top = top0; top > 0; top -= BWD_BATCH) {
         const int m = min(BWD_BATCH, top);
@@ -180,8 +181,9 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
                 const int j = c * 32 + __ffs(hits) - 1;
                 hits &= hits - 1;
                 const int pos = top - 1 - j; // index in the tile list == the reference's `contributor`
-                const float4 q0 = s_rec[4 * j];
-                const float4 q1 = s_rec[4 * j + 1];
+                const uint32_t rad = rec_base + 64u * (uint32_t)j;
+                const float4 q0 = lds128(rad);
+                const float4 q1 = lds128(rad + 16u);
                 const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
                 const float power = conic_power_b(q1.x, q1.y, q1.z, dx, dy);
                 const float G = expf(power);
@@ -193,7 +195,7 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
 #pragma unroll
                 for (int i = 0; i < 16; i++) v[i] = 0.f;
                 if (act) {
-                    const float4 q2 = s_rec[4 * j + 2], q3 = s_rec[4 * j + 3];
+                    const float4 q2 = lds128(rad + 32u), q3 = lds128(rad + 48u);
                     const float ra = rcp_approx(1.f - alpha);
                     T = T * ra;                       // transmittance in front of this splat
                     const float w = alpha * T;

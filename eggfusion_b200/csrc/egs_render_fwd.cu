@@ -70,6 +70,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
     const float pxf = (float)px, pyf = (float)py;
     const float tile_x0 = (float)(tx * EGS_TILE), tile_y0 = (float)(ty * EGS_TILE);
 
+    const uint32_t rec_base = smem_addr(s_rec);
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f;
     uint32_t last = 0;
     bool done = !inside;
@@ -96,8 +97,9 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                 const int j = c * 32 + __ffs(hits) - 1;
                 hits &= hits - 1;
                 if (done) continue;
-                const float4 q0 = s_rec[4 * j];
-                const float4 q1 = s_rec[4 * j + 1];
+                const uint32_t ra = rec_base + 64u * (uint32_t)j;
+                const float4 q0 = lds128(ra);
+                const float4 q1 = lds128(ra + 16u);
                 const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
                 const float power = conic_power(q1.x, q1.y, q1.z, dx, dy);
                 if (power > 0.0f) continue;
@@ -106,7 +108,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                 const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
                 if (test_T < 0.0001f) { done = true; continue; }
                 const float w = __fmul_rn(alpha, T);
-                const float4 q2 = s_rec[4 * j + 2], q3 = s_rec[4 * j + 3];
+                const float4 q2 = lds128(ra + 32u), q3 = lds128(ra + 48u);
                 const float dj = q1.w - (dx * q2.x + dy * q2.y);
                 D = fmaf(dj, w, D);
                 C0 = fmaf(q2.z, w, C0); C1 = fmaf(q2.w, w, C1); C2 = fmaf(q3.x, w, C2);

@@ -150,9 +150,22 @@ EGS_HD uint32_t pack_extent(float cov_xx, float cov_yy, float opacity) {
     return (uint32_t)qx | ((uint32_t)qy << 16);
 }
 
-// mean / scale / rot: this surfel's rows; color_src: SH block [M][3] (use_sh) or RGB triple.
+// Colour of a visible surfel: color_src = its SH block [M][3] (use_sh; may live in registers) or an RGB triple.
+EGS_HD void surfel_color(const FrameConst& fc, const float* mean, const float* color_src, bool use_sh, SurfelFwd& o) {
+    float rgb[3];
+    if (use_sh) {
+        o.clamped = sh_eval(fc.D, color_src, f_sub(mean[0], fc.campos[0]), f_sub(mean[1], fc.campos[1]),
+                            f_sub(mean[2], fc.campos[2]), rgb);
+    } else {
+        rgb[0] = color_src[0]; rgb[1] = color_src[1]; rgb[2] = color_src[2];
+    }
+    o.rec.r = rgb[0]; o.rec.g = rgb[1]; o.rec.b = rgb[2];
+}
+
+// Geometry of one surfel (mean / scale / rot: its rows).  Leaves o.radius == 0 when culled; the colour of a
+// visible surfel is filled in afterwards by surfel_color().
 EGS_HD void surfel_forward(const FrameConst& fc, const float* mean, const float* scale, const float* rot, float opacity,
-                           const float* color_src, bool use_sh, SurfelFwd& o) {
+                           SurfelFwd& o) {
     o.radius = 0;
     o.active = 0;
     o.clamped = 0;
@@ -248,12 +261,6 @@ EGS_HD void surfel_forward(const FrameConst& fc, const float* mean, const float*
     egs_tile_rect(ix, iy, rad, fc.gx, fc.gy, o.x0, o.y0, o.x1, o.y1);
     if ((o.x1 - o.x0) * (o.y1 - o.y0) == 0) return;
 
-    float rgb[3];
-    if (use_sh) {
-        o.clamped = sh_eval(fc.D, color_src, f_sub(px, fc.campos[0]), f_sub(py, fc.campos[1]), f_sub(pz, fc.campos[2]), rgb);
-    } else {
-        rgb[0] = color_src[0]; rgb[1] = color_src[1]; rgb[2] = color_src[2];
-    }
     o.radius = rad;
     SplatRecord& q = o.rec;
     q.x = ix; q.y = iy;
@@ -264,7 +271,7 @@ EGS_HD void surfel_forward(const FrameConst& fc, const float* mean, const float*
     // plane-depth slope: pos_dif.z of depth_differencing (auxiliary.h:283-290) is linear in the pixel offset
     q.ja = f_fma(J0, a0[2], f_mul(J2, a1[2]));
     q.jb = f_fma(J1, a0[2], f_mul(J3, a1[2]));
-    q.r = rgb[0]; q.g = rgb[1]; q.b = rgb[2];
+    q.r = 0.f; q.g = 0.f; q.b = 0.f;
     q.nx = nv[0]; q.ny = nv[1]; q.nz = nv[2];
 }
 

@@ -31,8 +31,8 @@ void emu_surfel_forward(int P, int W, int H, int D, int M, float tanfovx, float 
         SurfelFwd o;
         memset(&o, 0, sizeof(o));
         const bool use_sh = colors == nullptr;
-        surfel_forward(fc, means + 3 * i, scales + 3 * i, rots + 4 * i, opac[i],
-                       use_sh ? shs + (size_t)3 * M * i : colors + 3 * i, use_sh, o);
+        surfel_forward(fc, means + 3 * i, scales + 3 * i, rots + 4 * i, opac[i], o);
+        if (o.radius > 0) surfel_color(fc, means + 3 * i, use_sh ? shs + (size_t)3 * M * i : colors + 3 * i, use_sh, o);
         radii[i] = o.radius;
         active[i] = (uint8_t)o.active;
         if (o.radius > 0) {
