@@ -13,5 +13,7 @@ from .rasterizer import (  # noqa: F401
     cpu_deep_copy_tuple,
 )
 
-__all__ = ["build", "load", "GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
+from .fusion import preprocess_surfels, project_surfels_to_frame  # noqa: F401,E402
+
+__all__ = ["preprocess_surfels", "project_surfels_to_frame", "build", "load", "GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
            "cpu_deep_copy_tuple"]

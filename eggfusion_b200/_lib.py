@@ -42,6 +42,8 @@ SIGNATURES = {
     "egs_backward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),
     "egs_backward_surfels": (C.c_int, [C.POINTER(Frame), _I32, _I32] + [_P] * 17),
     "egs_mark_visible": (C.c_int, [_I32, _P, _P, _P, _P, _P]),
+    "egs_project_surfels": (C.c_int, [_I32, _I32, _I32] + [_P] * 10),
+    "egs_fuse_surfels": (C.c_int, [_I32, _I32, _I32] + [_P] * 13 + [C.c_float, C.c_float, C.c_float, _P]),
     "egs_debug_export": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _I64] + [_P] * 11),
 }
 

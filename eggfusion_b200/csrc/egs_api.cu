@@ -16,6 +16,12 @@ cudaError_t launch_render_forward(const egs_frame&, GeomView, ImgView, BinView, 
 cudaError_t launch_render_backward(const egs_frame&, GeomView, ImgView, BinView, long long, const float*, const float*,
                                    const float*, const float*, float*, cudaStream_t);
 
+cudaError_t launch_project_surfels(int, int, int, const float*, const float*, const uint8_t*, const float*, const float*,
+                                   const float*, unsigned long long*, int32_t*, float*, cudaStream_t);
+cudaError_t launch_fuse_surfels(int, int, int, const float*, const float*, const float*, const float*, const float*,
+                                const float*, const uint8_t*, const int32_t*, float*, float*, float*, uint8_t*, uint8_t*,
+                                float, float, float, cudaStream_t);
+
 namespace {
 inline int tiles_of(const egs_frame* f, int& gx, int& gy) {
     gx = (f->width + EGS_TILE - 1) / EGS_TILE;
@@ -165,6 +171,35 @@ EGS_API int egs_mark_visible(int32_t P, const float* means3D, const float* viewm
     if (P == 0) return 0;
     if (!means3D || !viewmatrix || !projmatrix || !present) return EGS_E_BADARG;
     EGS_TRY(launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream));
+    return 0;
+}
+
+EGS_API int egs_project_surfels(int32_t P, int32_t height, int32_t width, const float* points, const float* rotations,
+                                const uint8_t* stable_mask, const float* intrinsic, const float* viewmatrix,
+                                const float* projmatrix, void* scratch, int32_t* index_map, float* depth_buffer,
+                                void* stream) {
+    if (P < 0 || height <= 0 || width <= 0) return EGS_E_BADARG;
+    if (!scratch || !index_map || !depth_buffer || !intrinsic || !viewmatrix || !projmatrix) return EGS_E_BADARG;
+    if (P > 0 && (!points || !rotations || !stable_mask)) return EGS_E_BADARG;
+    EGS_TRY(launch_project_surfels(P, height, width, points, rotations, stable_mask, intrinsic, viewmatrix, projmatrix,
+                                   (unsigned long long*)scratch, index_map, depth_buffer, (cudaStream_t)stream));
+    return 0;
+}
+
+EGS_API int egs_fuse_surfels(int32_t P, int32_t height, int32_t width, const float* intrinsic, const float* viewmatrix,
+                             const float* projmatrix, const float* frame_vmap, const float* frame_nmap,
+                             const float* frame_dmap, const uint8_t* frame_mask, const int32_t* frame_imap,
+                             float* points, float* rotations, float* sigma2, uint8_t* inview_mask,
+                             uint8_t* surface_mask, float fusion_dist_thres, float alpha_p, float alpha_n,
+                             void* stream) {
+    if (P < 0 || height <= 0 || width <= 0) return EGS_E_BADARG;
+    if (P == 0) return 0;
+    if (!intrinsic || !viewmatrix || !projmatrix || !frame_vmap || !frame_nmap || !frame_dmap || !frame_mask ||
+        !frame_imap || !points || !rotations || !sigma2 || !inview_mask || !surface_mask)
+        return EGS_E_BADARG;
+    EGS_TRY(launch_fuse_surfels(P, height, width, intrinsic, viewmatrix, projmatrix, frame_vmap, frame_nmap, frame_dmap,
+                                frame_mask, frame_imap, points, rotations, sigma2, inview_mask, surface_mask,
+                                fusion_dist_thres, alpha_p, alpha_n, (cudaStream_t)stream));
     return 0;
 }
 

@@ -19,3 +19,4 @@ from eggfusion_b200.rasterizer import (  # noqa: E402,F401
     cpu_deep_copy_tuple,
     rasterize_gaussians,
 )
+from eggfusion_b200.fusion import preprocess_surfels, project_surfels_to_frame  # noqa: E402,F401

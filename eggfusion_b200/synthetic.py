@@ -188,3 +188,51 @@ def make_config(name: str, seed: int = SEED):
     P, W, H, L, deg = CONFIGS[name]
     cam = default_camera(W, H)
     return cam, make_scene(P, cam, layers=L, sh_degree=deg, seed=seed)
+
+
+def make_fusion_case(P: int, cam: Camera, seed: int = SEED + 7, alpha_p: float = 1.0, alpha_n: float = 0.5):
+    """Inputs of the once-per-frame fusion kernels (`project_surfels_to_frame`, `preprocess_surfels`):
+    a noisy copy of a one-sheet surfel model plus the frame's world-space vertex / normal / depth maps and masks
+    (what /root/reference/src/core/mapper.py:242-308 passes).  The camera pose is cam.w2c; maps are [H,W,C]."""
+    rng = np.random.default_rng(seed)
+    W, H = cam.width, cam.height
+    c2w = np.linalg.inv(cam.w2c.astype(np.float64))
+    # analytic depth sheet in the camera frame
+    v, u = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    depth_of = lambda uu, vv: 1.6 + 0.25 * np.sin(3 * uu / W) * np.cos(2 * vv / H)
+    z = depth_of(u, v)
+    vert_c = np.stack([(u - cam.cx) * z / cam.fx, (v - cam.cy) * z / cam.fy, z], axis=-1)
+    du = np.gradient(vert_c, axis=1)
+    dv = np.gradient(vert_c, axis=0)
+    n_c = np.cross(du, dv)
+    n_c /= np.linalg.norm(n_c, axis=-1, keepdims=True)
+    n_c[np.sum(n_c * vert_c, axis=-1) > 0] *= -1.0
+    vmap = vert_c @ c2w[:3, :3].T + c2w[:3, 3]
+    nmap = n_c @ c2w[:3, :3].T
+    mask = rng.uniform(size=(H, W)) > 0.03
+    holes = rng.uniform(size=(H, W)) < 0.02
+    nmap[holes] = 0.0                                    # invalid normals, as a depth sensor leaves them
+    dmap = z.copy()
+
+    # surfel model: points near the sheet (most within the fusion distance), normals near the sheet normal
+    us = rng.uniform(-0.08 * W, 1.08 * W, size=P)
+    vs = rng.uniform(-0.08 * H, 1.08 * H, size=P)
+    zs = depth_of(us, vs) + rng.normal(0, 0.012, size=P) + (rng.uniform(size=P) < 0.1) * rng.normal(0, 0.2, size=P)
+    pc = np.stack([(us - cam.cx) * zs / cam.fx, (vs - cam.cy) * zs / cam.fy, zs], axis=1)
+    pw = pc @ c2w[:3, :3].T + c2w[:3, 3]
+    iu = np.clip(np.rint(us), 0, W - 1).astype(int)
+    iv = np.clip(np.rint(vs), 0, H - 1).astype(int)
+    n = n_c[iv, iu] + rng.normal(0, 0.12, size=(P, 3))
+    wide = rng.uniform(size=P) < 0.08
+    n[wide] += rng.normal(0, 1.5, size=(int(wide.sum()), 3))   # some far-off normals: > 60 deg and back-facing ones
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    n_w = n @ c2w[:3, :3].T
+    q = _quat_z_to(n_w.astype(np.float64)) * rng.uniform(0.98, 1.02, size=(P, 1)).astype(np.float32)   # raw leaf params
+    sigma2 = np.stack([(zs * alpha_p) ** 2, (zs * alpha_n) ** 2], axis=1) * rng.uniform(0.3, 1.5, size=(P, 2))
+    stable = rng.uniform(size=P) < 0.8
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return {
+        "points": f32(pw), "rotations": f32(q), "sigma2": f32(sigma2), "stable_mask": stable,
+        "intrinsic": f32([cam.fx, cam.fy, cam.cx, cam.cy]), "frame_vmap": f32(vmap), "frame_nmap": f32(nmap),
+        "frame_dmap": f32(dmap), "frame_mask": mask, "fusion_dist_thres": 0.03, "alpha_p": alpha_p, "alpha_n": alpha_n,
+    }

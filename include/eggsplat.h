@@ -18,6 +18,8 @@
  *   egs_backward_render      BACKWARD::render (rasterizer_impl.cu:461-493, backward.cu:419-676)
  *   egs_backward_surfels     BACKWARD::preprocess (rasterizer_impl.cu:499-522, backward.cu:144-416)
  *   egs_mark_visible         Rasterizer::markVisible (rasterizer_impl.cu:145-157)
+ *   egs_project_surfels      projectSurfelsToFrame / ProjectSurfelsToFrameCUDA (DGS/fuse_surfels.cu:475-573)
+ *   egs_fuse_surfels         preprocessSurfel / PreprocessSurfelsFunctionCUDA (DGS/fuse_surfels.cu:214-471)
  *   egs_debug_export         (none: test hook that dumps the internal index artefacts for parity checks)
  *
  * Together egs_forward_plan + egs_forward_render are what `_C.rasterize_gaussians` binds
@@ -133,6 +135,33 @@ EGS_API int egs_backward_surfels(const egs_frame* frame, int32_t first, int32_t 
 /* present[i] = the coarse frustum test of the reference's markVisible (auxiliary.h:152-178). */
 EGS_API int egs_mark_visible(int32_t num_surfels, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);
+
+/*
+ * Index map of the global model in the current frame (`_C.project_surfels_to_frame`): every stable, in-frustum,
+ * front-facing surfel is splatted on the 3x3 pixels around its projection; per pixel the nearest surfel wins
+ * (ties: smallest index -- the race-free outcome of the reference's atomicMin + plain store).
+ * index_map [height][width] i32 and depth_buffer [height][width] f32 are updated in place where a nearer surfel is
+ * found (callers pre-fill them with -1 / +inf).  `scratch` = height*width*8 bytes of device memory.
+ * points [P][3], rotations [P][4] (raw quaternions w,x,y,z), stable_mask [P] bytes, intrinsic [4] = fx,fy,cx,cy.
+ */
+EGS_API int egs_project_surfels(int32_t num_surfels, int32_t height, int32_t width, const float* points,
+                                const float* rotations, const uint8_t* stable_mask, const float* intrinsic,
+                                const float* viewmatrix, const float* projmatrix, void* scratch, int32_t* index_map,
+                                float* depth_buffer, void* stream);
+
+/*
+ * In-place fusion of surfel position / normal with the current frame (`_C.preprocess_surfels`): mutates
+ * points [P][3], rotations [P][4], sigma2 [P][2]; writes inview_mask [P], surface_mask [P] (bytes).
+ * frame_vmap / frame_nmap [height][width][3], frame_dmap [height][width], frame_mask [height][width] bytes,
+ * frame_imap [height][width] i32 (from egs_project_surfels).  The reference kernel's unread arguments
+ * (scales, colours, confidence, tic, eta, counts, stable mask, depth buffer, model maps) are not part of the ABI.
+ */
+EGS_API int egs_fuse_surfels(int32_t num_surfels, int32_t height, int32_t width, const float* intrinsic,
+                             const float* viewmatrix, const float* projmatrix, const float* frame_vmap,
+                             const float* frame_nmap, const float* frame_dmap, const uint8_t* frame_mask,
+                             const int32_t* frame_imap, float* points, float* rotations, float* sigma2,
+                             uint8_t* inview_mask, uint8_t* surface_mask, float fusion_dist_thres, float alpha_p,
+                             float alpha_n, void* stream);
 
 /*
  * Test hook: copies internal index artefacts out of the workspaces into caller-provided DEVICE arrays

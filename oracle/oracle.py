@@ -173,3 +173,33 @@ def mark_visible(means, viewmatrix, projmatrix) -> np.ndarray:
         lib().egso_mark_visible(C.c_int(P), _p(means), _p(_f32(viewmatrix).reshape(-1)), _p(_f32(projmatrix).reshape(-1)),
                                 _p(out))
     return out.astype(bool)
+
+
+def project_surfels(points, rotations, stable_mask, intrinsic, viewmatrix, projmatrix, height, width):
+    """Oracle of project_surfels_to_frame: returns (index_map [h,w] i32, depth_buffer [h,w] f32)."""
+    points, rotations = _f32(points), _f32(rotations)
+    P = points.shape[0]
+    stable = np.ascontiguousarray(stable_mask, dtype=np.uint8)
+    index_map = np.full((height, width), -1, np.int32)
+    depth = np.full((height, width), np.inf, np.float32)
+    lib().egso_project_surfels(C.c_int(P), C.c_int(height), C.c_int(width), _p(points), _p(rotations), _p(stable),
+                               _p(_f32(intrinsic).reshape(-1)), _p(_f32(viewmatrix).reshape(-1)),
+                               _p(_f32(projmatrix).reshape(-1)), _p(index_map), _p(depth))
+    return index_map, depth
+
+
+def fuse_surfels(points, rotations, sigma2, intrinsic, viewmatrix, projmatrix, frame_vmap, frame_nmap, frame_dmap,
+                 frame_mask, frame_imap, fusion_dist_thres, alpha_p, alpha_n):
+    """Oracle of preprocess_surfels.  Returns copies: (points, rotations, sigma2, inview_mask, surface_mask)."""
+    points, rotations, sigma2 = _f32(points).copy(), _f32(rotations).copy(), _f32(sigma2).copy()
+    P = points.shape[0]
+    ht, wd = frame_nmap.shape[0], frame_nmap.shape[1]
+    inview, surface = np.zeros(P, np.uint8), np.zeros(P, np.uint8)
+    fm = np.ascontiguousarray(frame_mask, dtype=np.uint8)
+    im = np.ascontiguousarray(frame_imap, dtype=np.int32)
+    lib().egso_fuse_surfels(C.c_int(P), C.c_int(ht), C.c_int(wd), _p(_f32(intrinsic).reshape(-1)),
+                            _p(_f32(viewmatrix).reshape(-1)), _p(_f32(projmatrix).reshape(-1)), _p(_f32(frame_vmap)),
+                            _p(_f32(frame_nmap)), _p(_f32(frame_dmap)), _p(fm), _p(im), _p(points), _p(rotations),
+                            _p(sigma2), _p(inview), _p(surface), C.c_float(fusion_dist_thres), C.c_float(alpha_p),
+                            C.c_float(alpha_n))
+    return points, rotations, sigma2, inview.astype(bool), surface.astype(bool)

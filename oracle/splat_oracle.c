@@ -912,3 +912,177 @@ void egso_set_num_threads(int n) {
     (void)n;
 #endif
 }
+
+/* ================================================================================================
+ * Surfel fusion kernels: /root/reference/submodules/diff-gaussian-surfels/fuse_surfels.cu
+ * ================================================================================================ */
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int rn_int(float x) { return (int)nearbyintf(x); } /* __float2int_rn */
+static inline int rd_int(float x) { return (int)floorf(x); }    /* __float2int_rd */
+
+/* shared front part of both kernels: projection, frustum test, rotation, back-face test.
+ * Returns 0 when the surfel is rejected; *stage = 1 once it passed the frustum test. */
+static int fuse_common(const float* view, const float* proj, int wd, int ht, float cx, float cy, const float* p,
+                       const float* q, float pc[3], float coord[2], float Rg[3][3], float zaxis[3]) {
+    float hx = affine_row(proj, 0, p[0], p[1], p[2]), hy = affine_row(proj, 1, p[0], p[1], p[2]);
+    float hw = affine_row(proj, 3, p[0], p[1], p[2]);
+    float pw = 1.0f / (hw + 0.0000001f);
+    for (int r = 0; r < 3; r++) pc[r] = affine_row(view, r, p[0], p[1], p[2]);
+    coord[0] = (float)fma((double)((hx * pw) * (float)wd), 0.5, (double)cx);
+    coord[1] = (float)fma((double)((hy * pw) * (float)ht), 0.5, (double)cy);
+    const float e = 0.05f;
+    float x0 = (float)(-wd) * e, x1 = (float)wd * (1 + e), y0 = (float)(-ht) * e, y1 = (float)ht * (1 + e);
+    if (pc[2] < 0 || coord[0] < x0 || coord[0] >= x1 || coord[1] < y0 || coord[1] >= y1) return 0;
+    quat_to_Rg(q, Rg);
+    for (int r = 0; r < 3; r++) zaxis[r] = linear_row(view, r, Rg[0][2], Rg[1][2], Rg[2][2]);
+    float facing = dot3c(pc[0], zaxis[0], pc[1], zaxis[1], pc[2], zaxis[2]);
+    if ((double)facing > -0.00001) return 0;
+    return 1;
+}
+
+/*
+ * projectSurfelsToFrame (fuse_surfels.cu:475-536): z-buffer of stable, front-facing surfels splatted on a 3x3
+ * pixel footprint.  The reference races (atomicMin on the depth, then a plain store of the index); this is the
+ * race-free outcome: per pixel the smallest depth, ties to the smallest surfel index.
+ * index_map[ht*wd] must be pre-filled with -1, depth_buffer[ht*wd] with +inf (reference __init__.py:316-317).
+ */
+void egso_project_surfels(int P, int ht, int wd, const float* points, const float* rotations, const uint8_t* stable,
+                          const float* intrinsic, const float* view, const float* proj, int32_t* index_map,
+                          float* depth_buffer) {
+    const float cx = intrinsic[2], cy = intrinsic[3];
+    for (int i = 0; i < P; i++) {
+        if (!stable[i]) continue;
+        float pc[3], coord[2], Rg[3][3], z[3];
+        if (!fuse_common(view, proj, wd, ht, cx, cy, points + 3 * i, rotations + 4 * i, pc, coord, Rg, z)) continue;
+        int x = (int)coord[0], y = (int)coord[1];
+        if (x < 0 || x >= wd || y < 0 || y >= ht) continue;
+        float depth = pc[2];
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                int nx = x + dx, ny = y + dy;
+                if (nx < 0 || nx >= wd || ny < 0 || ny >= ht) continue;
+                int k = ny * wd + nx;
+                if (depth < depth_buffer[k]) {
+                    depth_buffer[k] = depth;
+                    index_map[k] = i;
+                }
+            }
+    }
+}
+
+static int all4_nonzero_f(const float* map, int wd, int x, int y, int ch) {
+    for (int c = 0; c < ch; c++) {
+        if (map[(y * wd + x) * ch + c] == 0) return 0;
+        if (map[(y * wd + x + 1) * ch + c] == 0) return 0;
+        if (map[((y + 1) * wd + x) * ch + c] == 0) return 0;
+        if (map[((y + 1) * wd + x + 1) * ch + c] == 0) return 0;
+    }
+    return 1;
+}
+
+/*
+ * preprocessSurfel (fuse_surfels.cu:214-394): in-place information-filter fusion of surfel position / normal
+ * with the current frame.  Mutates points[P][3], rotations[P][4] (raw, un-normalised quaternions), sigma2[P][2];
+ * writes inview_mask[P], surface_mask[P].  frame_vmap / frame_nmap are [ht][wd][3], frame_dmap [ht][wd],
+ * frame_mask [ht][wd] (bool bytes), frame_imap [ht][wd] i32.  The arguments the reference kernel receives but
+ * never reads (scales, colors, confidence, tic, eta, counts, stable mask, depth buffer, model maps) are omitted.
+ */
+void egso_fuse_surfels(int P, int ht, int wd, const float* intrinsic, const float* view, const float* proj,
+                       const float* frame_vmap, const float* frame_nmap, const float* frame_dmap,
+                       const uint8_t* frame_mask, const int32_t* frame_imap, float* points, float* rotations,
+                       float* sigma2, uint8_t* inview, uint8_t* surface, float dist_thres, float alpha_p,
+                       float alpha_n) {
+    const float cx = intrinsic[2], cy = intrinsic[3];
+    for (int i = 0; i < P; i++) {
+        inview[i] = 0;
+        surface[i] = 0;
+        float pw[3] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+        float pc[3], coord[2], R[3][3], zax[3];
+        if (!fuse_common(view, proj, wd, ht, cx, cy, pw, rotations + 4 * i, pc, coord, R, zax)) continue;
+        inview[i] = 1;
+        {   /* is_valid on the normal map (3 channels) and on the mask (fuse_surfels.cu:166-212) */
+            int x = rd_int(coord[0]), y = rd_int(coord[1]);
+            if (x < 0 || x + 1 >= wd || y < 0 || y + 1 >= ht) continue;
+            if (!all4_nonzero_f(frame_nmap, wd, x, y, 3)) continue;
+            if (!frame_mask[y * wd + x] || !frame_mask[y * wd + x + 1] || !frame_mask[(y + 1) * wd + x] ||
+                !frame_mask[(y + 1) * wd + x + 1])
+                continue;
+        }
+        int ix = clampi(rn_int(coord[0]), 0, wd - 1), iy = clampi(rn_int(coord[1]), 0, ht - 1);
+        int nidx = iy * wd + ix;
+        float nw[3] = {R[0][2], R[1][2], R[2][2]};
+        {
+            float inv = 1.0f / sqrtf(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
+            nw[0] *= inv; nw[1] *= inv; nw[2] *= inv;
+        }
+        float nc[3] = {frame_nmap[3 * nidx], frame_nmap[3 * nidx + 1], frame_nmap[3 * nidx + 2]};
+        {
+            float inv = 1.0f / sqrtf(nc[0] * nc[0] + nc[1] * nc[1] + nc[2] * nc[2]);
+            nc[0] *= inv; nc[1] *= inv; nc[2] *= inv;
+        }
+        float vc[3] = {frame_vmap[3 * nidx], frame_vmap[3 * nidx + 1], frame_vmap[3 * nidx + 2]};
+        float vd[3] = {pw[0] - vc[0], pw[1] - vc[1], pw[2] - vc[2]};
+        int sid = frame_imap[rn_int(coord[1]) * wd + rn_int(coord[0])];
+        if (sid >= 0 && sid == i) surface[i] = 1;
+        if (sqrtf(vd[0] * vd[0] + vd[1] * vd[1] + vd[2] * vd[2]) > dist_thres) continue;
+
+        float s2p = sigma2[2 * i], s2n = sigma2[2 * i + 1];
+        float eta_p[3] = {pw[0] / s2p, pw[1] / s2p, pw[2] / s2p};
+        float eta_n[3] = {nw[0] / s2n, nw[1] / s2n, nw[2] / s2n};
+        float d = frame_dmap[nidx];
+        float s2pz = (alpha_p * d) * (alpha_p * d), s2nz = (alpha_n * d) * (alpha_n * d);
+        float s2p_new = 1.f / (1.f / s2pz + 1.f / s2p), s2n_new = 1.f / (1.f / s2nz + 1.f / s2n);
+        float lp = 1.f / s2pz, ln = 1.f / s2nz;
+        float xn[3];
+        for (int k = 0; k < 3; k++) {
+            points[3 * i + k] = s2p_new * (eta_p[k] + lp * vc[k]);
+            xn[k] = s2n_new * (eta_n[k] + ln * nc[k]);
+        }
+        sigma2[2 * i] = s2p_new;
+
+        float dotn = nw[0] * nc[0] + nw[1] * nc[1] + nw[2] * nc[2];
+        dotn = dotn > 1 ? 1 : (dotn < -1 ? -1 : dotn);
+        double angle = (double)(acosf(dotn) * 180) / 3.1415926;
+        if (!(angle < 60)) continue;
+        float inv = 1.0f / sqrtf(xn[0] * xn[0] + xn[1] * xn[1] + xn[2] * xn[2]);
+        float nn[3] = {xn[0] * inv, xn[1] * inv, xn[2] * inv};
+        float cr[3] = {nw[1] * nn[2] - nw[2] * nn[1], nw[2] * nn[0] - nw[0] * nn[2], nw[0] * nn[1] - nw[1] * nn[0]};
+        inv = 1.0f / sqrtf(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+        float n12[3] = {cr[0] * inv, cr[1] * inv, cr[2] * inv};
+        float ct = nw[0] * nn[0] + nw[1] * nn[1] + nw[2] * nn[2];
+        ct = ct > 1 ? 1 : (ct < -1 ? -1 : ct);
+        double theta = (double)(acosf(ct) * 180) / 3.1415926;
+        if (theta < 1) continue;
+        /* rotvec2rotmatrix (fuse_surfels.cu:64-89); the vector is normalised again inside */
+        float ang = acosf(ct);
+        float nrm = sqrtf(n12[0] * n12[0] + n12[1] * n12[1] + n12[2] * n12[2]);
+        float ux = n12[0] / nrm, uy = n12[1] / nrm, uz = n12[2] / nrm;
+        float c = cosf(ang), s = sinf(ang);
+        float R1[3][3];
+        R1[0][0] = c + ux * ux * (1 - c);      R1[0][1] = ux * uy * (1 - c) - uz * s; R1[0][2] = ux * uz * (1 - c) + uy * s;
+        R1[1][0] = uy * ux * (1 - c) + uz * s; R1[1][1] = c + uy * uy * (1 - c);      R1[1][2] = uy * uz * (1 - c) - ux * s;
+        R1[2][0] = uz * ux * (1 - c) - uy * s; R1[2][1] = uz * uy * (1 - c) + ux * s; R1[2][2] = c + uz * uz * (1 - c);
+        /* glm R * R1 with both stored "transposed": in usual indexing R2 = R1 . R */
+        float R2[3][3];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) R2[a][b] = R[0][b] * R1[a][0] + R[1][b] * R1[a][1] + R[2][b] * R1[a][2];
+        /* rotmat2quaternion (fuse_surfels.cu:31-62) */
+        float tr = R2[0][0] + R2[1][1] + R2[2][2], qw, qx, qy, qz;
+        if (tr > 0.0f) {
+            float ss = 0.5f / sqrtf(tr + 1.0f);
+            qw = 0.25f / ss; qx = (R2[2][1] - R2[1][2]) * ss; qy = (R2[0][2] - R2[2][0]) * ss; qz = (R2[1][0] - R2[0][1]) * ss;
+        } else if (R2[0][0] > R2[1][1] && R2[0][0] > R2[2][2]) {
+            float ss = 2.0f * sqrtf(1.0f + R2[0][0] - R2[1][1] - R2[2][2]);
+            qw = (R2[2][1] - R2[1][2]) / ss; qx = 0.25f * ss; qy = (R2[0][1] + R2[1][0]) / ss; qz = (R2[0][2] + R2[2][0]) / ss;
+        } else if (R2[1][1] > R2[2][2]) {
+            float ss = 2.0f * sqrtf(1.0f + R2[1][1] - R2[0][0] - R2[2][2]);
+            qw = (R2[0][2] - R2[2][0]) / ss; qx = (R2[0][1] + R2[1][0]) / ss; qy = 0.25f * ss; qz = (R2[1][2] + R2[2][1]) / ss;
+        } else {
+            float ss = 2.0f * sqrtf(1.0f + R2[2][2] - R2[0][0] - R2[1][1]);
+            qw = (R2[1][0] - R2[0][1]) / ss; qx = (R2[0][2] + R2[2][0]) / ss; qy = (R2[1][2] + R2[2][1]) / ss; qz = 0.25f * ss;
+        }
+        rotations[4 * i] = qw; rotations[4 * i + 1] = qx; rotations[4 * i + 2] = qy; rotations[4 * i + 3] = qz;
+        sigma2[2 * i + 1] = s2n_new;
+    }
+}

@@ -95,6 +95,43 @@ def run_reference(name, device="cuda"):
     return out
 
 
+FUSION_CASES = {
+    # name: (P, W, H, pose)
+    "fusion_320x240": (20_000, 320, 240, ((0.05, -0.02, 0.03), 0.04, -0.03)),
+}
+
+
+def fusion_inputs(name):
+    P, W, H, pose = FUSION_CASES[name]
+    cam = syn.default_camera(W, H, syn.look_from(*pose))
+    return cam, syn.make_fusion_case(P, cam)
+
+
+def run_reference_fusion(name, device="cuda"):
+    """_C.project_surfels_to_frame + _C.preprocess_surfels of the unmodified reference."""
+    ref = ref_loader.load()
+    cam, fc = fusion_inputs(name)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    P = fc["points"].shape[0]
+    pts, rot, s2 = t(fc["points"]), t(fc["rotations"]), t(fc["sigma2"])
+    stable = t(fc["stable_mask"])
+    intr, view, proj = t(fc["intrinsic"]), t(cam.viewmatrix), t(cam.projmatrix)
+    imap, dbuf = ref.project_surfels_to_frame(pts, rot, stable, intr, view, proj, 1.0, cam.height, cam.width)
+    torch.cuda.synchronize()
+    z = lambda *shape, dt=torch.float32: torch.zeros(*shape, dtype=dt, device=device)
+    inview, surface = z(P, dt=torch.bool), z(P, dt=torch.bool)
+    ref.preprocess_surfels(pts, rot, z(P, 3), z(P, 3), z(P), z(P, dt=torch.int32), z(P, 6), s2, z(P, dt=torch.int32),
+                           z(P, dt=torch.int32), stable, intr, view, proj, t(fc["frame_vmap"]), t(fc["frame_nmap"]),
+                           z(cam.height, cam.width, 3), t(fc["frame_dmap"]), t(fc["frame_mask"]), imap, dbuf,
+                           z(cam.height, cam.width, 3), z(cam.height, cam.width, 3),
+                           z(cam.height, cam.width, dt=torch.bool), inview, surface, fc["fusion_dist_thres"],
+                           fc["alpha_p"], fc["alpha_n"])
+    torch.cuda.synchronize()
+    return {"index_map": imap.cpu().numpy(), "depth_buffer": dbuf.cpu().numpy(), "points": pts.cpu().numpy(),
+            "rotations": rot.cpu().numpy(), "sigma2": s2.cpu().numpy(), "inview_mask": inview.cpu().numpy(),
+            "surface_mask": surface.cpu().numpy()}
+
+
 def main():
     outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(outdir, exist_ok=True)
@@ -107,6 +144,11 @@ def main():
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
         print(name, "I=%d tiles=%d vis=%d" % (out["num_rendered"], out["tile_num"], len(out["vis_index"])),
               "size=%.2f MB" % (os.path.getsize(os.path.join(outdir, name + ".npz")) / 1e6))
+    for name in FUSION_CASES:
+        out = run_reference_fusion(name)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
+        print(name, "index hits %.3f inview %.3f surface %.3f" % ((out["index_map"] >= 0).mean(),
+                                                                  out["inview_mask"].mean(), out["surface_mask"].mean()))
 
 
 if __name__ == "__main__":

@@ -291,3 +291,30 @@ def test_mark_visible_rule():
     pts = np.array([[0, 0, 1.0], [0, 0, 0.1], [5, 0, 1.0], [0, 0, -1.0], [0.5, 0.3, 1.0]], np.float32)
     vis = orc.mark_visible(pts, cam.viewmatrix, cam.projmatrix)
     assert vis.tolist() == [True, False, False, False, True]
+
+
+def test_fusion_oracle_matches_reference_golden():
+    """project_surfels_to_frame / preprocess_surfels: oracle vs the unmodified reference (B200 golden)."""
+    path = util.golden_path("fusion_320x240")
+    assert os.path.exists(path)
+    G = np.load(path)
+    cam, fc = util.fusion_inputs()
+    imap, dbuf = orc.project_surfels(fc["points"], fc["rotations"], fc["stable_mask"], fc["intrinsic"], cam.viewmatrix,
+                                     cam.projmatrix, cam.height, cam.width)
+    assert np.array_equal(dbuf.view(np.uint32), G["depth_buffer"].view(np.uint32))
+    bad = imap != G["index_map"]
+    assert bad.mean() <= 0.01
+    z = fc["points"] @ cam.viewmatrix[:3, 2] + cam.viewmatrix[3, 2]
+    assert (z[G["index_map"][bad]] > dbuf[bad]).all()        # the reference's differing ids are stale (its race)
+    p, r, s2, inv, surf = orc.fuse_surfels(fc["points"], fc["rotations"], fc["sigma2"], fc["intrinsic"],
+                                           cam.viewmatrix, cam.projmatrix, fc["frame_vmap"], fc["frame_nmap"],
+                                           fc["frame_dmap"], fc["frame_mask"], G["index_map"],
+                                           fc["fusion_dist_thres"], fc["alpha_p"], fc["alpha_n"])
+    assert np.array_equal(inv, G["inview_mask"]) and np.array_equal(surf, G["surface_mask"])
+    moved = np.abs(p - fc["points"]).max(1) > 0
+    assert np.array_equal(moved, np.abs(G["points"] - fc["points"]).max(1) > 0)
+    rotated = np.abs(r - fc["rotations"]).max(1) > 0
+    assert np.array_equal(rotated, np.abs(G["rotations"] - fc["rotations"]).max(1) > 0)
+    assert moved.mean() > 0.3 and rotated.mean() > 0.3 and surf.mean() > 0.1
+    assert rel_err(p, G["points"]) <= 1e-6 and rel_err(s2, G["sigma2"]) <= 1e-6
+    assert np.abs(r - G["rotations"]).max() <= 2e-5

@@ -82,3 +82,7 @@ def screen_block_from_oracle(b, P):
     sg[:, 9:12] = b["dL_dnormal"]
     sg[:, 12] = b["dL_ddepth"][:, 0]
     return sg
+
+
+def fusion_inputs(name="fusion_320x240"):
+    return _golden_mod().fusion_inputs(name)
