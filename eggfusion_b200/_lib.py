@@ -47,6 +47,16 @@ SIGNATURES = {
     "egs_debug_export": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _I64] + [_P] * 11),
 }
 
+# include/eggtrack.h
+SIGNATURES.update({
+    "egt_bilateral_filter": (C.c_int, [_P, _P, _I32, _I32, _I32, C.c_float, C.c_float, _P]),
+    "egt_gaussian_filter": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, C.c_float, _P]),
+    "egt_gaussian_downsample": (C.c_int, [_P, _P, _I32, _I32, _I32, _P]),
+    "egt_compute_gradients": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
+    "egt_vertex_normal_map": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _I32, _I32, _P]),
+    "egt_solve_block": (C.c_int, [_P, _P, C.c_float, _P, _I32, _P]),
+})
+
 _lib = None
 
 

@@ -14,11 +14,25 @@ if [ ! -d "$SRC" ]; then
     exit 0
 fi
 if ls "$OUT"/diff_gaussian_rasterization/_C*.so >/dev/null 2>&1 && [ -z "${FORCE:-}" ]; then
-    echo "oracle/_ref already built"; exit 0
-fi
+    echo "oracle/_ref rasterizer already built"
+else
 rm -rf "$WORK" && mkdir -p "$WORK" && cp -r "$SRC/." "$WORK/" && chmod -R u+w "$WORK"
 ( cd "$WORK" && NVCC_APPEND_FLAGS="-include cstdint" TORCH_CUDA_ARCH_LIST="10.0a" MAX_JOBS="${MAX_JOBS:-8}" \
       python setup.py build_ext --inplace > build.log 2>&1 ) || { tail -30 "$WORK/build.log"; exit 1; }
 mkdir -p "$OUT/diff_gaussian_rasterization"
 cp "$WORK"/diff_gaussian_rasterization/__init__.py "$WORK"/diff_gaussian_rasterization/_C*.so "$OUT/diff_gaussian_rasterization/"
-echo "built $OUT"
+fi
+echo "built $OUT (rasterizer)"
+
+# --- the dense-tracking util (src/utils/cuda): one .cu file; needs <Eigen/Dense> only for its host-side solveBlock.
+# Eigen is not installed here, so a stub header (oracle/stubs/Eigen/Dense) lets the unmodified file compile; its CUDA
+# kernels (what the goldens use) are untouched, solveBlock aborts if called.
+TRK_SRC="${REFERENCE_ROOT:-/root/reference}/src/utils/cuda"
+if [ -d "$TRK_SRC" ] && ! ls "$OUT"/cuda_tracking_ext*.so >/dev/null 2>&1; then
+    TW="${REF_BUILD_DIR:-/tmp/dgs_ref_build}_trk"
+    rm -rf "$TW" && mkdir -p "$TW" && cp -r "$TRK_SRC/." "$TW/" && chmod -R u+w "$TW"
+    ( cd "$TW" && CPLUS_INCLUDE_PATH="$HERE/stubs" NVCC_APPEND_FLAGS="-I$HERE/stubs" TORCH_CUDA_ARCH_LIST="10.0a" \
+          MAX_JOBS="${MAX_JOBS:-8}" python setup.py build_ext --inplace > build.log 2>&1 ) || { tail -30 "$TW/build.log"; exit 1; }
+    cp "$TW"/cuda_tracking_ext*.so "$OUT/"
+    echo "built $OUT (tracking util, Eigen stubbed)"
+fi

@@ -203,3 +203,55 @@ def fuse_surfels(points, rotations, sigma2, intrinsic, viewmatrix, projmatrix, f
                             _p(sigma2), _p(inview), _p(surface), C.c_float(fusion_dist_thres), C.c_float(alpha_p),
                             C.c_float(alpha_n))
     return points, rotations, sigma2, inview.astype(bool), surface.astype(bool)
+
+
+# ------------------------------------------------------------------------------------------- tracking utilities
+def bilateral_filter(img, window, sigma_color, sigma_space):
+    img = _f32(img)
+    ht, wd = img.shape[:2]
+    out = np.zeros_like(img)
+    lib().egto_bilateral(_p(img), _p(out), C.c_int(wd), C.c_int(ht), C.c_int(window), C.c_float(sigma_color),
+                         C.c_float(sigma_space))
+    return out
+
+
+def gaussian_filter(img, window, sigma):
+    img = _f32(img)
+    ht, wd, ch = img.shape
+    out = np.zeros_like(img)
+    lib().egto_gaussian(_p(img), _p(out), C.c_int(wd), C.c_int(ht), C.c_int(ch), C.c_int(window), C.c_float(sigma))
+    return out
+
+
+def gaussian_downsample(img):
+    img = _f32(img)
+    ht, wd, ch = img.shape
+    out = np.zeros((ht // 2, wd // 2, ch), np.float32)
+    lib().egto_downsample(_p(img), _p(out), C.c_int(wd), C.c_int(ht), C.c_int(ch))
+    return out
+
+
+def compute_gradient(img):
+    img = _f32(img)
+    ht, wd = img.shape[:2]
+    gx, gy = np.zeros((ht, wd), np.float32), np.zeros((ht, wd), np.float32)
+    lib().egto_gradients(_p(img), _p(gx), _p(gy), C.c_int(wd), C.c_int(ht))
+    return gx, gy
+
+
+def compute_vertex_and_normal(depth, fx, fy, cx, cy):
+    depth = _f32(depth)
+    ht, wd = depth.shape[:2]
+    vmap, nmap = np.zeros((ht, wd, 3), np.float32), np.zeros((ht, wd, 3), np.float32)
+    lib().egto_vertex_normal(_p(depth), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(vmap), _p(nmap),
+                             C.c_int(wd), C.c_int(ht))
+    return vmap, nmap
+
+
+def solve_block(A, b, lm):
+    """solveBlock (TRK:929-950) is Eigen's colPivHouseholderQr of (A + lm I) on the CPU; Eigen is not vendored in
+    the reference nor installed here, so this restates it as a float64 least-squares solve (parity unpinned for
+    this one function: the reference's Eigen build could not be run)."""
+    A = np.asarray(A, np.float64)
+    n = A.shape[0]
+    return np.linalg.lstsq(A + lm * np.eye(n), np.asarray(b, np.float64).reshape(n), rcond=None)[0].astype(np.float32)

@@ -1086,3 +1086,122 @@ void egso_fuse_surfels(int P, int ht, int wd, const float* intrinsic, const floa
         sigma2[2 * i + 1] = s2n_new;
     }
 }
+
+/* ================================================================================================
+ * Dense-tracking image utilities: /root/reference/src/utils/cuda/src/tracking.cu ("TRK")
+ * ================================================================================================ */
+
+/* bilateral_filter_kernel (TRK:777-821) */
+void egto_bilateral(const float* in, float* out, int wd, int ht, int window, float sigma_c, float sigma_s) {
+    const float ss = 1.0f / (2.0f * sigma_s * sigma_s), sc = 1.0f / (2.0f * sigma_c * sigma_c);
+    const int r = window / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < ht; y++)
+        for (int x = 0; x < wd; x++) {
+            float c = in[y * wd + x], s1 = 0.f, s2 = 0.f;
+            for (int dy = -r; dy <= r; dy++)
+                for (int dx = -r; dx <= r; dx++) {
+                    int nx = x + dx, ny = y + dy;
+                    if (nx < 0 || nx >= wd || ny < 0 || ny >= ht) continue;
+                    float v = in[ny * wd + nx], dc = c - v;
+                    float space2 = (float)(dx * dx + dy * dy), color2 = dc * dc;
+                    float w = expf(-space2 * ss - color2 * sc);
+                    s1 += v * w;
+                    s2 += w;
+                }
+            out[y * wd + x] = s1 / s2;
+        }
+}
+
+/* gaussian_filter_kernel (TRK:705-751) */
+void egto_gaussian(const float* in, float* out, int wd, int ht, int ch, int window, float sigma_s) {
+    const float ss = 1.0f / (2.0f * sigma_s * sigma_s);
+    const int r = window / 2;
+    for (int y = 0; y < ht; y++)
+        for (int x = 0; x < wd; x++) {
+            float s1[4] = {0, 0, 0, 0}, s2 = 0.f;
+            for (int dy = -r; dy <= r; dy++)
+                for (int dx = -r; dx <= r; dx++) {
+                    int nx = x + dx, ny = y + dy;
+                    if (nx < 0 || nx >= wd || ny < 0 || ny >= ht) continue;
+                    float w = expf(-(float)(dx * dx + dy * dy) * ss);
+                    for (int c = 0; c < ch; c++) s1[c] += in[(ny * wd + nx) * ch + c] * w;
+                    s2 += w;
+                }
+            for (int c = 0; c < ch; c++) out[(y * wd + x) * ch + c] = s1[c] / s2;
+        }
+}
+
+/* gaussian_downsample_kernel (TRK:533-575) with the 5x5 table of TRK:585-586 */
+void egto_downsample(const float* in, float* out, int wd, int ht, int ch) {
+    static const float k[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
+    const int dw = wd / 2, dh = ht / 2;
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            float sum[4] = {0, 0, 0, 0}, count = 0.f;
+            for (int dy = -2; dy <= 2; dy++)
+                for (int dx = -2; dx <= 2; dx++) {
+                    int nx = 2 * x + dx, ny = 2 * y + dy;
+                    if (nx < 0 || nx >= wd || ny < 0 || ny >= ht) continue;
+                    float w = k[(dy + 2) * 5 + (dx + 2)];
+                    for (int c = 0; c < ch; c++) sum[c] += in[(ny * wd + nx) * ch + c] * w;
+                    count += w;
+                }
+            for (int c = 0; c < ch; c++) out[(y * dw + x) * ch + c] = sum[c] / count;
+        }
+}
+
+/* gradient_kernel (TRK:853-893) with the tables of TRK:903-909, walked from index 8 down to 0 */
+void egto_gradients(const float* in, float* gx, float* gy, int wd, int ht) {
+    static const float kx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+    static const float ky[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+    for (int y = 0; y < ht; y++)
+        for (int x = 0; x < wd; x++) {
+            float ax = 0.f, ay = 0.f;
+            int k = 8;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int nx = x + dx, ny = y + dy;
+                    if (nx >= 0 && nx < wd && ny >= 0 && ny < ht) {
+                        float v = in[ny * wd + nx];
+                        ax += v * kx[k];
+                        ay += v * ky[k];
+                    }
+                    --k;
+                }
+            gx[y * wd + x] = ax;
+            gy[y * wd + x] = ay;
+        }
+}
+
+/* compute_vertex_map_kernel + compute_normal_map_kernel (TRK:602-672) */
+void egto_vertex_normal(const float* depth, float fx, float fy, float cx, float cy, float* vmap, float* nmap, int wd,
+                        int ht) {
+    for (int y = 0; y < ht; y++)
+        for (int x = 0; x < wd; x++) {
+            int i = y * wd + x;
+            float Z = depth[i];
+            vmap[3 * i] = ((float)x - cx) * Z / fx;
+            vmap[3 * i + 1] = ((float)y - cy) * Z / fy;
+            vmap[3 * i + 2] = Z;
+        }
+    for (int y = 0; y < ht; y++)
+        for (int x = 0; x < wd; x++) {
+            int i = y * wd + x;
+            const float* v00 = vmap + 3 * i;
+            const float* v10 = (x + 1 < wd) ? vmap + 3 * (i + 1) : v00;
+            const float* v01 = (y + 1 < ht) ? vmap + 3 * (i + wd) : v00;
+            float a[3] = {v01[0] - v00[0], v01[1] - v00[1], v01[2] - v00[2]};
+            float b[3] = {v10[0] - v00[0], v10[1] - v00[1], v10[2] - v00[2]};
+            /* nvcc contracts x*y - u*v into fma(x, y, -(u*v)): for parallel a, b (both neighbours are holes) the
+             * result is the rounding error of one product, not 0, and the reference then emits a unit vector */
+            float n[3] = {fmaf(a[1], b[2], -(a[2] * b[1])), fmaf(a[2], b[0], -(a[0] * b[2])),
+                          fmaf(a[0], b[1], -(a[1] * b[0]))};
+            float d2 = fmaf(n[2], n[2], fmaf(n[0], n[0], n[1] * n[1]));
+            if (d2 < 1.17549435e-38f) d2 = 0.f; /* rsqrtf (rsqrt.approx.ftz) flushes denormal inputs to zero */
+            float inv = 1.0f / sqrtf(d2);
+            n[0] *= inv; n[1] *= inv; n[2] *= inv;
+            if (isnan(n[0]) || isnan(n[1]) || isnan(n[2])) n[0] = n[1] = n[2] = 0.f;
+            nmap[3 * i] = n[0]; nmap[3 * i + 1] = n[1]; nmap[3 * i + 2] = n[2];
+        }
+}

@@ -132,6 +132,59 @@ def run_reference_fusion(name, device="cuda"):
             "surface_mask": surface.cpu().numpy()}
 
 
+def tracking_inputs(seed=20251209, W=161, H=119):
+    """Deterministic frame for the dense-tracking utilities (odd sizes exercise the borders)."""
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    depth = 1.5 + 0.4 * np.sin(u / 17.0) * np.cos(v / 11.0) + 0.002 * rng.normal(size=(H, W))
+    depth[(u > 100) & (v < 30)] += 0.8                      # a depth discontinuity
+    depth[rng.uniform(size=(H, W)) < 0.02] = 0.0            # sensor holes
+    gray = 0.5 + 0.3 * np.sin(u / 5.0 + v / 9.0) + 0.05 * rng.normal(size=(H, W))
+    rgb = np.stack([gray, 0.8 * gray + 0.1, 1.0 - gray], axis=-1)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return {"depth": f32(depth), "gray": f32(gray), "rgb": f32(rgb), "intr": (140.0, 138.0, 80.3, 59.1)}
+
+
+def load_ref_tracking():
+    """The reference's cuda_tracking_ext built by oracle/build_ref.sh (Eigen stubbed: kernels only)."""
+    import glob
+    import importlib.util as iu
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "cuda_tracking_ext*.so"))
+    if not so:
+        return None
+    spec = iu.spec_from_file_location("cuda_tracking_ext", so[0])
+    mod = iu.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_reference_tracking(device="cuda"):
+    ext = load_ref_tracking()
+    ti = tracking_inputs()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    depth, gray, rgb = t(ti["depth"]), t(ti["gray"]), t(ti["rgb"])
+    H, W = depth.shape
+    fx, fy, cx, cy = ti["intr"]
+    out = {}
+    o = torch.zeros_like(depth)
+    ext.bilateral_filter_cuda(depth, o, W, H, 13, 0.03, 4.5)
+    out["bilateral"] = o.cpu().numpy()
+    o = torch.zeros_like(rgb)
+    ext.gaussian_filter_cuda(rgb, o, W, H, 3, 5, 1.5)
+    out["gaussian"] = o.cpu().numpy()
+    for name, img in (("down1", gray[..., None].contiguous()), ("down3", rgb)):
+        o = torch.zeros(H // 2, W // 2, img.shape[2], device=device)
+        ext.gaussian_downsample_cuda(img, o, W, H, img.shape[2])
+        out[name] = o.cpu().numpy()
+    gx, gy = torch.zeros_like(gray), torch.zeros_like(gray)
+    ext.compute_gradients_cuda(gray, gx, gy, W, H)
+    out["grad_x"], out["grad_y"] = gx.cpu().numpy(), gy.cpu().numpy()
+    vm, nm = torch.zeros(H, W, 3, device=device), torch.zeros(H, W, 3, device=device)
+    ext.compute_vertex_and_normal_cuda(depth, fx, fy, cx, cy, vm, nm)
+    out["vertex"], out["normal"] = vm.cpu().numpy(), nm.cpu().numpy()
+    return out
+
+
 def main():
     outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(outdir, exist_ok=True)
@@ -144,6 +197,9 @@ def main():
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
         print(name, "I=%d tiles=%d vis=%d" % (out["num_rendered"], out["tile_num"], len(out["vis_index"])),
               "size=%.2f MB" % (os.path.getsize(os.path.join(outdir, name + ".npz")) / 1e6))
+    if load_ref_tracking() is not None:
+        np.savez_compressed(os.path.join(outdir, "tracking_161x119.npz"), **run_reference_tracking())
+        print("tracking_161x119 written")
     for name in FUSION_CASES:
         out = run_reference_fusion(name)
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)

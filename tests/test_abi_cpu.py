@@ -10,21 +10,21 @@ import torch
 
 from util import ROOT
 
-HEADER = os.path.join(ROOT, "include", "eggsplat.h")
+HEADERS = [os.path.join(ROOT, "include", "eggsplat.h"), os.path.join(ROOT, "include", "eggtrack.h")]
 
 
 def declared_symbols():
-    src = open(HEADER).read()
-    return sorted(set(re.findall(r"EGS_API\s+[\w\s\*]+?\b(egs_\w+)\s*\(", src)))
+    src = "".join(open(h).read() for h in HEADERS)
+    return sorted(set(re.findall(r"EGS_API\s+[\w\s\*]+?\b(eg[st]_\w+)\s*\(", src)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():
     import eggfusion_b200
     so = eggfusion_b200.build()
     out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
-    exported = sorted(set(re.findall(r"\bT\s+(egs_\w+)", out)))
+    exported = sorted(set(re.findall(r"\bT\s+(eg[st]_\w+)", out)))
     decl = declared_symbols()
-    assert len(decl) >= 9
+    assert len(decl) >= 17
     assert exported == decl
 
 
@@ -62,8 +62,13 @@ def test_python_api_mirrors_reference_names():
     try:
         import diff_gaussian_rasterization as D
         for name in ("GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
-                     "cpu_deep_copy_tuple"):
+                     "cpu_deep_copy_tuple", "preprocess_surfels", "project_surfels_to_frame"):
             assert hasattr(D, name)
+        import cuda_tracking_ext as T
+        for name in ("projective_transform_cuda", "rgb_optimization_cuda", "icp_optimization_cuda",
+                     "compute_vertex_and_normal_cuda", "gaussian_filter_cuda", "bilateral_filter_cuda",
+                     "gaussian_downsample_cuda", "compute_gradients_cuda", "solve_block_cuda"):
+            assert hasattr(T, name)      # the nine exports of tracking.cu:952-962
     finally:
         sys.path.pop(0)
 

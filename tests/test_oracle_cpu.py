@@ -318,3 +318,24 @@ def test_fusion_oracle_matches_reference_golden():
     assert moved.mean() > 0.3 and rotated.mean() > 0.3 and surf.mean() > 0.1
     assert rel_err(p, G["points"]) <= 1e-6 and rel_err(s2, G["sigma2"]) <= 1e-6
     assert np.abs(r - G["rotations"]).max() <= 2e-5
+
+
+def test_tracking_oracle_matches_reference_golden():
+    """Dense-tracking image utilities: oracle vs the reference's own kernels (tracking.cu compiled with a stub
+    Eigen header, run on B200).  solve_block has no reference pin (Eigen is absent): it is checked against numpy."""
+    path = util.golden_path("tracking_161x119")
+    assert os.path.exists(path)
+    G = np.load(path)
+    ti = util.tracking_inputs()
+    fx, fy, cx, cy = ti["intr"]
+    ref = {"bilateral": orc.bilateral_filter(ti["depth"], 13, 0.03, 4.5), "gaussian": orc.gaussian_filter(ti["rgb"], 5, 1.5),
+           "down1": orc.gaussian_downsample(ti["gray"][..., None]), "down3": orc.gaussian_downsample(ti["rgb"])}
+    ref["grad_x"], ref["grad_y"] = orc.compute_gradient(ti["gray"])
+    ref["vertex"], ref["normal"] = orc.compute_vertex_and_normal(ti["depth"], fx, fy, cx, cy)
+    for k in ("bilateral", "gaussian", "down1", "down3", "grad_x", "grad_y"):
+        assert rel_err(ref[k], G[k]) <= 1e-6, k
+    assert np.array_equal(ref["vertex"].view(np.uint32), G["vertex"].view(np.uint32))
+    assert np.array_equal(np.all(ref["normal"] == 0, -1), np.all(G["normal"] == 0, -1))
+    assert np.abs(ref["normal"] - G["normal"]).max() <= 1e-6
+    A = np.diag(np.arange(1, 7)).astype(np.float32)
+    np.testing.assert_allclose(orc.solve_block(A, np.ones(6, np.float32), 0.0), 1.0 / np.arange(1, 7), rtol=1e-6)

@@ -86,3 +86,7 @@ def screen_block_from_oracle(b, P):
 
 def fusion_inputs(name="fusion_320x240"):
     return _golden_mod().fusion_inputs(name)
+
+
+def tracking_inputs():
+    return _golden_mod().tracking_inputs()
