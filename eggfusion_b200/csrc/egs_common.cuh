@@ -5,7 +5,8 @@
 //                                 tiles_touched[P] u32 | clamped[P] u8
 //   img  workspace:               egs_counters (+ticket) | tile_count[T] | tile_offset[T+1] | tile_cursor[T] |
 //                                 tile_list[T] (compacted non-empty tiles) | final_T[N] | final_D[N] | n_contrib[N]
-//   bin  workspace, per instance: keys[cap] u64 (depth bits << 32 | surfel id, bucketed by tile) | point_list[cap] u32
+//   bin  workspace, per instance: keys[cap] u64 (depth bits << 32 | surfel id, bucketed by tile) | point_list[cap] u32 |
+//                                 lane_masks[cap][8] u32 (which pixels of each 8x4 warp block blended the instance)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -99,6 +100,7 @@ struct ImgView {
 struct BinView {
     unsigned long long* keys;
     uint32_t* point_list;
+    uint32_t* lane_masks; // [cap][8]: bit l of word w = pixel l of warp block w blended this instance in the forward
     size_t bytes;
 };
 
@@ -135,6 +137,7 @@ EGS_HD BinView carve_bin(void* base, size_t cap) {
     char* b = (char*)base;
     v.keys = (unsigned long long*)(b + o);  o = egs_align_up(o + 8 * cap, 256);
     v.point_list = (uint32_t*)(b + o);      o = egs_align_up(o + 4 * cap, 256);
+    v.lane_masks = (uint32_t*)(b + o);      o = egs_align_up(o + 32 * cap, 256);
     v.bytes = o + 256;
     return v;
 }

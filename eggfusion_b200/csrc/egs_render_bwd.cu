@@ -3,9 +3,11 @@
 // Replaces renderCUDA<3> backward (DGS/cuda_rasterizer/backward.cu:419-676), which issues 13 float atomicAdds
 // per contributing (pixel, surfel) pair.  This kernel is bound by instruction issue, not by HBM (ncu: DRAM < 2 %),
 // so the design minimises warp-instructions per (tile, surfel):
-//   * a warp owns an 8x4 pixel block.  While a batch of splat records is staged into shared memory, the staging
-//     thread of each record computes which of the 8 blocks its alpha >= 1/255 ellipse box can reach (one byte);
-//     a warp then walks only its own hits (ballot over the mask bytes + find-first-set), front of the list last;
+//   * a warp owns an 8x4 pixel block.  The forward saved, per (instance, warp block), the 32-bit mask of pixels
+//     that blended it; a warp walks only instances with a non-zero mask (ballot + find-first-set, back of the list
+//     first) and each lane reads its bit instead of repeating the power / alpha / transmittance tests.  (Those
+//     pairs are exactly the reference's `contributor < last_contributor && power <= 0 && alpha >= 1/255`: a
+//     pixel is never `done` before its last contributor.)  With no decision left, exp() is one MUFU.EX2;
 //   * the reference's 14 running accumulators (accum_rec / last_* for 3 colour, 3 normal, 1 depth channels) are
 //     folded into ONE scalar per pixel.  With kappa_j = sum_ch feature_ch(j) * dL/dpixel_ch and
 //     sigma_j = sum_{k behind j} w_k kappa_k, the reference's
@@ -27,6 +29,12 @@ __device__ __forceinline__ float conic_power_b(float cxx, float cxy, float cyy, 
     const float q = __fmaf_rn(__fmul_rn(cxx, dx), dx, __fmul_rn(__fmul_rn(cyy, dy), dy));
     const float dist = __fmaf_rn(__fmul_rn(__fmul_rn(2.f, cxy), dx), dy, q);
     return __fmul_rn(-0.5f, dist);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -78,25 +86,13 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
     v[0] += __shfl_xor_sync(full, v[0], 1);
 }
 
-// Which of the tile's 8 warp blocks (2 columns x 4 rows of 8x4 pixels) can the record's extent box reach?
-__device__ __forceinline__ uint32_t block_mask(float x, float y, uint32_t ext, float tile_x0, float tile_y0) {
-    const float hx = (float)(ext & 0xffffu) * 0.125f + 3.5f, hy = (float)(ext >> 16) * 0.125f + 1.5f;
-    const float rx = x - tile_x0, ry = y - tile_y0;
-    const uint32_t xm = (fabsf(rx - 3.5f) <= hx ? 1u : 0u) | (fabsf(rx - 11.5f) <= hx ? 2u : 0u);
-    uint32_t m = 0;
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-        if (fabsf(ry - (1.5f + 4.f * r)) <= hy) m |= xm << (2 * r);
-    return m;
-}
-
-__global__ void __launch_bounds__(EGS_TILE_THREADS, 3)
+__global__ void __launch_bounds__(EGS_TILE_THREADS, 4)
 k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
                   BinView bn, long long cap, const float* __restrict__ gC, const float* __restrict__ gN,
                   const float* __restrict__ gDp, const float* __restrict__ gOp, float* __restrict__ sg) {
     __shared__ float4 s_rec[BWD_BATCH * 4];
     __shared__ uint32_t s_id[BWD_BATCH];
-    __shared__ uint32_t s_wm[BWD_BATCH];
+    __shared__ __align__(16) uint32_t s_lm[BWD_BATCH * 8];
     __shared__ __align__(16) float s_part[BWD_WARPS][BWD_BATCH][16];
     __shared__ unsigned long long s_mask[BWD_WARPS];
     __shared__ int s_top;
@@ -117,7 +113,6 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
     const size_t pix = (size_t)W * py + px;
     const uint32_t* __restrict__ plist = bn.point_list + start;
     const float pxf = (float)px, pyf = (float)py;
-    const float tile_x0 = (float)(tx * EGS_TILE), tile_y0 = (float)(ty * EGS_TILE);
 
     if (threadIdx.x == 0) s_top = 0;
     __syncthreads();
@@ -164,32 +159,32 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
             s_rec[threadIdx.x * 4] = a; s_rec[threadIdx.x * 4 + 1] = b;
             s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
-            s_wm[threadIdx.x] = block_mask(a.x, a.y, __float_as_uint(a.z), tile_x0, tile_y0);
+            const uint4* lm = reinterpret_cast<const uint4*>(bn.lane_masks + 8 * (size_t)(start + top - 1 - (int)threadIdx.x));
+            reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x] = __ldg(lm);
+            reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x + 1] = __ldg(lm + 1);
         } else if (threadIdx.x < BWD_BATCH) {
-            s_wm[threadIdx.x] = 0u;
+            reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
 
         unsigned long long wmask = 0ull;
 #pragma unroll
         for (int c = 0; c < BWD_BATCH / 32; c++) {
-            // entry j of the batch is list position top-1-j (back to front); skip what nobody in this warp blended
+            // entry j of the batch is list position top-1-j (back to front)
             const int jl = c * 32 + lane;
-            const bool mine = (s_wm[jl] >> warp & 1u) && (top - 1 - jl) < warp_last;
-            unsigned hits = __ballot_sync(0xffffffffu, mine);
+            unsigned hits = __ballot_sync(0xffffffffu, s_lm[8 * jl + warp] != 0u);
             while (hits) {
                 const int j = c * 32 + __ffs(hits) - 1;
                 hits &= hits - 1;
-                const int pos = top - 1 - j; // index in the tile list == the reference's `contributor`
+                const bool act = (s_lm[8 * j + warp] >> lane) & 1u;
                 const uint32_t rad = rec_base + 64u * (uint32_t)j;
                 const float4 q0 = lds128(rad);
                 const float4 q1 = lds128(rad + 16u);
                 const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
                 const float power = conic_power_b(q1.x, q1.y, q1.z, dx, dy);
-                const float G = expf(power);
-                const float alpha = fminf(0.99f, __fmul_rn(q0.w, G));
-                const bool act = pos < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                if (!__any_sync(0xffffffffu, act)) continue;
+                const float G = ex2_approx(power * 1.4426950408889634f);
+                const float alpha = fminf(0.99f, q0.w * G);
 
                 float v[16];
 #pragma unroll

@@ -8,7 +8,9 @@
 //     staged, the staging thread of each record computes which of the 8 blocks its alpha >= 1/255 ellipse box
 //     can reach (one mask word); a warp then visits only its own hits (ballot + find-first-set).  The kernel is
 //     issue-bound (ncu: 89 % issue-active, DRAM 2 %), so instructions per (tile, surfel) are what matters;
-//   * splats are staged as packed 64-byte records (one gather per instance instead of eight).
+//   * splats are staged as packed 64-byte records (one gather per instance instead of eight);
+//   * for every (instance, warp block) the 32-bit mask of pixels that actually blended it is saved (32 B per
+//     instance): the backward walks exactly those pairs and never repeats the alpha / transmittance tests.
 // Per pixel the arithmetic order of the reference is kept: power, alpha = min(0.99, o*exp(power)), skip < 1/255,
 // stop (without blending) when T(1-alpha) < 1e-4, w = alpha*T, fma accumulation, T clamp at 1-1e-6.
 #include "egs_common.cuh"
@@ -34,12 +36,13 @@ __device__ __forceinline__ uint32_t block_mask_f(float x, float y, uint32_t ext,
     return m;
 }
 
-__global__ void __launch_bounds__(EGS_TILE_THREADS)
+__global__ void __launch_bounds__(EGS_TILE_THREADS, 6)
 k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
                  BinView bn, long long cap, float* __restrict__ out_color, float* __restrict__ out_normal,
                  float* __restrict__ out_depth, float* __restrict__ out_opac) {
     __shared__ float4 s_rec[FWD_BATCH * 4];
     __shared__ uint32_t s_wm[FWD_BATCH];
+    __shared__ __align__(16) uint32_t s_lm[FWD_BATCH * 8];
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
@@ -88,35 +91,48 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
             wm = block_mask_f(a.x, a.y, __float_as_uint(a.z), tile_x0, tile_y0);
         }
         s_wm[threadIdx.x] = wm;
+        reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x + 1] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;
-        const int chunks = (m + 31) >> 5;
-        for (int c = 0; c < chunks; c++) {
-            unsigned hits = __ballot_sync(0xffffffffu, (s_wm[c * 32 + lane] >> warp) & 1u);
-            while (hits) {
-                const int j = c * 32 + __ffs(hits) - 1;
-                hits &= hits - 1;
-                if (done) continue;
-                const uint32_t ra = rec_base + 64u * (uint32_t)j;
-                const float4 q0 = lds128(ra);
-                const float4 q1 = lds128(ra + 16u);
-                const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
-                const float power = conic_power(q1.x, q1.y, q1.z, dx, dy);
-                if (power > 0.0f) continue;
-                const float alpha = fminf(0.99f, __fmul_rn(q0.w, expf(power)));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
-                if (test_T < 0.0001f) { done = true; continue; }
-                const float w = __fmul_rn(alpha, T);
-                const float4 q2 = lds128(ra + 32u), q3 = lds128(ra + 48u);
-                const float dj = q1.w - (dx * q2.x + dy * q2.y);
-                D = fmaf(dj, w, D);
-                C0 = fmaf(q2.z, w, C0); C1 = fmaf(q2.w, w, C1); C2 = fmaf(q3.x, w, C2);
-                N0 = fmaf(q3.y, w, N0); N1 = fmaf(q3.z, w, N1); N2 = fmaf(q3.w, w, N2);
-                T = test_T;
-                last = (uint32_t)(base + j + 1);
+        if (!__all_sync(0xffffffffu, done)) {
+            const int chunks = (m + 31) >> 5;
+            for (int c = 0; c < chunks; c++) {
+                unsigned hits = __ballot_sync(0xffffffffu, (s_wm[c * 32 + lane] >> warp) & 1u);
+                while (hits) {
+                    const int j = c * 32 + __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const uint32_t ra = rec_base + 64u * (uint32_t)j;
+                    const float4 q0 = lds128(ra);
+                    const float4 q1 = lds128(ra + 16u);
+                    const float dx = __fsub_rn(q0.x, pxf), dy = __fsub_rn(q0.y, pyf);
+                    const float power = conic_power(q1.x, q1.y, q1.z, dx, dy);
+                    const float alpha = fminf(0.99f, __fmul_rn(q0.w, expf(power)));
+                    const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+                    bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    if (ok && test_T < 0.0001f) { done = true; ok = false; }   // stops WITHOUT blending this one
+                    const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                    if (bm == 0u) continue;
+                    if (lane == 0) s_lm[8 * j + warp] = bm;
+                    if (ok) {
+                        const float w = __fmul_rn(alpha, T);
+                        const float4 q2 = lds128(ra + 32u), q3 = lds128(ra + 48u);
+                        const float dj = q1.w - (dx * q2.x + dy * q2.y);
+                        D = fmaf(dj, w, D);
+                        C0 = fmaf(q2.z, w, C0); C1 = fmaf(q2.w, w, C1); C2 = fmaf(q3.x, w, C2);
+                        N0 = fmaf(q3.y, w, N0); N1 = fmaf(q3.z, w, N1); N2 = fmaf(q3.w, w, N2);
+                        T = test_T;
+                        last = (uint32_t)(base + j + 1);
+                    }
+                }
+                if (__all_sync(0xffffffffu, done)) break;
             }
-            if (__all_sync(0xffffffffu, done)) break;
+        }
+        __syncthreads();
+        // publish the blend masks of this batch: 32 contiguous bytes per instance
+        if ((int)threadIdx.x < m) {
+            uint4* dst = reinterpret_cast<uint4*>(bn.lane_masks + 8 * (size_t)(start + base + threadIdx.x));
+            dst[0] = reinterpret_cast<const uint4*>(s_lm)[2 * threadIdx.x];
+            dst[1] = reinterpret_cast<const uint4*>(s_lm)[2 * threadIdx.x + 1];
         }
     }
     if (inside) {
