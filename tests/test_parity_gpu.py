@@ -313,3 +313,25 @@ def test_properties_at_full_size():
         acc = g2["screen"].clone() if acc is None else acc + g2["screen"]
     assert torch.equal(img_sum, color)
     assert rel_err(acc.cpu().numpy(), full["screen"].cpu().numpy()) <= 1e-5
+
+
+def test_backward_kernel_variants_agree():
+    """EGS_BWD_KERNEL=mma (tensor-core reduction, 3xTF32) must match the default shuffle-butterfly kernel."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_parity_gpu as T\n"
+        "o = T.cuda_run('c1_posed_bg')\n"
+        "np.save(sys.argv[1], o['g_screen'])\n"
+    ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
+    outs = {}
+    for variant in ("butterfly", "mma"):
+        path = "/tmp/egs_variant_%s.npy" % variant
+        env = dict(os.environ, EGS_BWD_KERNEL=variant)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=util.ROOT)
+        outs[variant] = np.load(path)
+    assert rel_err(outs["mma"], outs["butterfly"]) <= 2e-5
+    cam, sc, g, bg, mask, deg, f, b = util.oracle_run("c1_posed_bg")
+    sg = util.screen_block_from_oracle(b, sc["xyz"].shape[0])
+    assert rel_err(outs["mma"], sg) <= TOL
