@@ -245,16 +245,20 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
 cudaError_t launch_render_backward_mma(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
                                        const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                        cudaStream_t s);
+cudaError_t launch_render_backward_gather(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
+                                          const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
+                                          cudaStream_t s);
 
-// Two implementations of the same walk: cross-pixel sums with the shuffle butterfly (default) or on the tensor
-// cores via mma.sync 3xTF32 (EGS_BWD_KERNEL=mma).  Measured on B200 at C3: butterfly 1.38 ms, mma 1.62 ms -- the
-// legacy mma.sync path costs more issue slots than it saves here; it is kept for A/B measurements and is covered by
-// the parity tests.
+// Three implementations of the same walk, selected with EGS_BWD_KERNEL (default: gather).  Measured on B200 at C3:
+//   gather     transposed FP32 reduction + cp.async double-buffered staging (egs_render_bwd_gather.cu)   1.15 ms
+//   butterfly  16-shuffle transposing butterfly + shared-memory combine (this file)                      1.38 ms
+//   mma        cross-pixel sums on the tensor cores, mma.sync 3xTF32 (egs_render_bwd_mma.cu)             1.62 ms
+// The legacy mma.sync path costs more issue slots than it saves here.  All three are covered by the parity tests.
 static int bwd_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("EGS_BWD_KERNEL");
-        v = (e && e[0] == 'm') ? 1 : 0;
+        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : 2;
     }
     return v;
 }
@@ -263,6 +267,7 @@ cudaError_t launch_render_backward(const egs_frame& f, GeomView g, ImgView im, B
                                    const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                    cudaStream_t s) {
     if (bwd_variant() == 1) return launch_render_backward_mma(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
+    if (bwd_variant() == 2) return launch_render_backward_gather(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
     const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
     k_render_backward<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, gC, gN, gD,
                                                            gO, sg);
