@@ -337,3 +337,63 @@ def test_backward_kernel_variants_agree():
     sg = util.screen_block_from_oracle(b, sc["xyz"].shape[0])
     assert rel_err(outs["mma"], sg) <= TOL
     assert rel_err(outs["gather"], sg) <= TOL
+
+
+def _random_case(seed, P, W, H, deg, layers=3, big=False, dense_tile=False):
+    """Seeded random scene + posed camera + gradients for the fuzz tests."""
+    from eggfusion_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    base = syn.default_camera(W, H)
+    sc = syn.make_scene(P, base, layers=layers, sh_degree=deg, seed=seed)
+    if big:        # a few very large surfels: radius clamps, rectangles covering the whole grid
+        sc["scales"][: max(1, P // 50), :2] *= 40.0
+    if dense_tile:  # pile every surfel onto a few pixels: one tile list far beyond the shared-memory sort capacity
+        sc["xyz"][:, 0] *= 0.02
+        sc["xyz"][:, 1] *= 0.02
+        sc["scales"][:, :2] *= 0.3
+    pose = syn.look_from(tuple(rng.uniform(-0.1, 0.1, size=3)), float(rng.uniform(-0.1, 0.1)), float(rng.uniform(-0.1, 0.1)))
+    cam = syn.default_camera(W, H, pose)
+    g = syn.make_pixel_grads(cam, seed=seed + 1, with_opacity=True)
+    bg = rng.uniform(0, 1, size=3).astype(np.float32)
+    return cam, sc, g, bg
+
+
+@pytest.mark.parametrize("seed,P,W,H,deg,kw", [
+    (101, 1500, 97, 61, 3, {}),                       # odd image size, partial tiles on both borders
+    (102, 800, 15, 9, 2, {}),                         # image smaller than one tile
+    (103, 1200, 130, 70, 1, {"big": True}),           # huge splats
+    (104, 9000, 48, 48, 0, {"dense_tile": True}),     # > 4096 instances in one tile: global-memory sort path
+    (105, 2500, 320, 200, 3, {"layers": 6}),
+])
+def test_fuzz_against_oracle(seed, P, W, H, deg, kw):
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R
+    from oracle import oracle as orc
+    cam, sc, g, bg = _random_case(seed, P, W, H, deg, **kw)
+    M = sc["shs"].shape[1]
+    oc = orc.cam_from_synthetic(cam, deg, M, bg=bg)
+    f = orc.forward(oc, sc["xyz"], sc["scales"], sc["rotations"], sc["opacity"], sc["shs"])
+    b = orc.backward(oc, f, sc["xyz"], sc["scales"], sc["rotations"], sc["shs"], g["color"], g["normal"], g["depth"],
+                     g["opacity"])
+    s = _settings(E, cam, bg, deg)
+    empty = torch.Tensor([])
+    means, shs, opac = _t(sc["xyz"]), _t(sc["shs"]), _t(sc["opacity"])
+    scales, rots = _t(sc["scales"]), _t(sc["rotations"])
+    color, normal, depth, opacity, active, radii, st = R.forward_raw(s, means, shs, empty, opac, scales, rots, None)
+    dbg = R.debug_export(st, P, W, H)
+    gr = R.backward_raw(st, means, shs, empty, scales, rots, _t(g["color"]), _t(g["normal"]), _t(g["depth"]),
+                        _t(g["opacity"]))
+    if kw.get("dense_tile"):
+        lens = f["ranges"][:, 1].astype(np.int64) - f["ranges"][:, 0]
+        assert lens.max() > 4096, "case does not reach the global-memory sort path"
+    assert np.array_equal(radii.cpu().numpy(), f["radii"])
+    assert st.num_rendered == f["num_rendered"]
+    assert np.array_equal(dbg["point_list"].cpu().numpy().astype(np.uint32), f["point_list"])
+    assert np.array_equal(dbg["ranges"].cpu().numpy().astype(np.uint32), f["ranges"])
+    assert rel_err(color.cpu().numpy(), f["color"]) <= TOL
+    assert rel_err(depth.cpu().numpy(), f["depth"]) <= TOL
+    assert rel_err(normal.cpu().numpy(), f["out_normal"]) <= TOL
+    assert rel_err(opacity.cpu().numpy(), f["opacity"]) <= TOL
+    for mine, theirs in (("means3D", "dL_dmeans3D"), ("sh", "dL_dsh"), ("scales", "dL_dscales"),
+                         ("rotations", "dL_drotations"), ("opacities", "dL_dopacity")):
+        assert rel_err(gr[mine].cpu().numpy().reshape(-1), b[theirs].reshape(-1)) <= TOL, mine
