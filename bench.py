@@ -131,24 +131,26 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline_sample(scene, cam, grad, deg, rows_mod=2):
-    """Oracle port (C, OpenMP) on a bounded sample: every `rows_mod`-th tile row of the workload's first camera."""
+def cpu_baseline_sample(scene, cams, grads, deg, budget_s=12.0):
+    """Oracle port (C, OpenMP, all host cores) on a bounded sample of the same workload: whole frames (forward +
+    backward) of the workload's cameras, as many as fit in ~`budget_s` seconds (at least one)."""
     from oracle import oracle as orc
     M = scene["shs"].shape[1]
-    oc = orc.cam_from_synthetic(cam, deg, M)
-    ty, tx = cam.tiles
-    mask = np.zeros((ty, tx), np.int32)
-    mask[::rows_mod, :] = 1
+    I_tot, frames = 0, 0
     t0 = time.perf_counter()
-    f = orc.forward(oc, scene["xyz"], scene["scales"], scene["rotations"], scene["opacity"], scene["shs"],
-                    tile_mask=mask)
-    orc.backward(oc, f, scene["xyz"], scene["scales"], scene["rotations"], scene["shs"], grad["color"],
-                 grad["normal"], grad["depth"], grad["opacity"])
+    for cam, grad in zip(cams, grads):
+        oc = orc.cam_from_synthetic(cam, deg, M)
+        f = orc.forward(oc, scene["xyz"], scene["scales"], scene["rotations"], scene["opacity"], scene["shs"])
+        orc.backward(oc, f, scene["xyz"], scene["scales"], scene["rotations"], scene["shs"], grad["color"],
+                     grad["normal"], grad["depth"], grad["opacity"])
+        I_tot += f["num_rendered"]
+        frames += 1
+        if time.perf_counter() - t0 > budget_s * (frames / (frames + 1.0)):
+            break
     dt = time.perf_counter() - t0
-    I = f["num_rendered"]
-    return {"value": 256.0 * I / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "sample": "1 fwd+bwd of camera 0, every %d-th tile row (%d of %d tile rows, %d instances), %.1f s"
-                      % (rows_mod, len(range(0, ty, rows_mod)), ty, I, dt)}
+    return {"value": 256.0 * I_tot / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "frames_per_s": frames / dt,
+            "sample": "%d full frame(s) fwd+bwd (cameras 0..%d, %d instances) in %.1f s" % (frames, frames - 1, I_tot, dt)}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -325,6 +327,8 @@ def run_ours(args):
         dom_kernel, dom_bytes = "k_render_forward(+k_emit,k_tile_sort)", ab["emit_sort"] + ab["render_forward"]
     else:
         dom_kernel, dom_bytes = "k_" + kern_of[dom_stage], ab[kern_of[dom_stage]]
+        if dom_stage == "bwd_render":
+            dom_kernel = "k_render_backward_" + os.environ.get("EGS_BWD_KERNEL", "gather")
     achieved = dom_bytes / (stage_ms[dom_stage] * 1e-3) / 1e9
     traffic = None
     try:  # DRAM bytes of the same kernel from the committed ncu capture of this workload (profiles/)
@@ -355,7 +359,7 @@ def run_ours(args):
         "e2e": e2e,
     }
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_sample(scene, cams[0], grads[0], deg)
+        line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -378,7 +382,7 @@ def run_reference(args):
         pass
     if not have_gpu_ref:
         # no compiled reference on this box: time the CPU port of its algorithm on a bounded sample
-        cb = cpu_baseline_sample(scene, cams[0], grads[0], deg)
+        cb = cpu_baseline_sample(scene, cams, grads, deg)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
                           "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
