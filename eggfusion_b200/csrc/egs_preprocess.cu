@@ -5,15 +5,43 @@
 // (DGS/cuda_rasterizer/backward.cu:144-416) and checkFrustum (DGS/cuda_rasterizer/rasterizer_impl.cu:54-66).
 #include "egs_surfel_math.cuh"
 
-__global__ void __launch_bounds__(128)
+#define SURF_THREADS 128
+#define SH_PITCH 49   // floats per staged SH row (48 + 1: conflict-free 4-byte accesses, one row per thread)
+
+// Coalesced copy of this CTA's `rows` SH rows (48 floats each, contiguous in global memory) into shared memory.
+__device__ __forceinline__ void stage_sh_rows(float* s_sh, const float* __restrict__ src, int rows) {
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (int idx = threadIdx.x; idx < rows * 12; idx += SURF_THREADS) {
+        const float4 v = __ldg(src4 + idx);
+        float* d = s_sh + (idx / 12) * SH_PITCH + 4 * (idx % 12);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+}
+__device__ __forceinline__ void unstage_sh_rows(const float* s_sh, float* __restrict__ dst, int rows) {
+    float4* dst4 = reinterpret_cast<float4*>(dst);
+    for (int idx = threadIdx.x; idx < rows * 12; idx += SURF_THREADS) {
+        const float* d = s_sh + (idx / 12) * SH_PITCH + 4 * (idx % 12);
+        dst4[idx] = make_float4(d[0], d[1], d[2], d[3]);
+    }
+}
+
+// SH_SMEM: the CTA's SH block (M == 16: 128 x 192 B, contiguous) is staged through shared memory with fully
+// coalesced 16-byte loads and read on demand, instead of living in 48 registers per thread.
+template <bool SH_SMEM>
+__global__ void __launch_bounds__(SURF_THREADS)
 k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
                  const float* __restrict__ colors, const int32_t* __restrict__ tile_mask, GeomView g, ImgView im,
                  int32_t* __restrict__ radii, uint8_t* __restrict__ active) {
     __shared__ FrameConst fc;
+    __shared__ float s_sh[SH_SMEM ? SURF_THREADS * SH_PITCH : 1];
     load_frame_const(fc, f);
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (SH_SMEM) {
+        const int row0 = blockIdx.x * SURF_THREADS;
+        stage_sh_rows(s_sh, shs + (size_t)48 * row0, min(SURF_THREADS, f.num_surfels - row0));
+    }
+    __syncthreads();
     const bool valid = i < f.num_surfels;
     bool visible = false;
     if (valid) {
@@ -26,9 +54,10 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
         uint32_t cnt = 0;
         if (o.radius > 0) {
             visible = true;
-            if (use_sh) {
-                // this surfel's SH block: 3*(D+1)^2 floats, fetched as 16-byte vectors when the rows allow it
-                // (the scalar pattern costs 32 L1 wavefronts per 4 bytes: it made this kernel L1-bound)
+            if (SH_SMEM) {
+                surfel_color(fc, mean, s_sh + threadIdx.x * SH_PITCH, true, o);
+            } else if (use_sh) {
+                // generic layout: this surfel's 3*(D+1)^2 floats into registers (16-byte vectors when rows allow it)
                 float shreg[48];
                 const float* src = shs + (size_t)3 * fc.M * i;
                 const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
@@ -73,7 +102,8 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(128)
+template <bool SH_SMEM>
+__global__ void __launch_bounds__(SURF_THREADS)
 k_surfel_backward(const egs_frame f, int first, int count, const float* __restrict__ means,
                   const float* __restrict__ shs, const float* __restrict__ colors, const float* __restrict__ scales,
                   const float* __restrict__ rots, const int32_t* __restrict__ radii, GeomView g,
@@ -81,91 +111,112 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
                   float* __restrict__ d_sh, float* __restrict__ d_scales, float* __restrict__ d_rots,
                   float* __restrict__ d_means2D, float* __restrict__ d_colors, float* __restrict__ d_cov3D) {
     __shared__ FrameConst fc;
+    __shared__ float s_sh[SH_SMEM ? SURF_THREADS * SH_PITCH : 1];
     load_frame_const(fc, f);
-    __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
+    const int row0 = first + blockIdx.x * SURF_THREADS;
+    const int rows = min(SURF_THREADS, first + count - row0);
+    if (SH_SMEM) stage_sh_rows(s_sh, shs + (size_t)48 * row0, rows);
+    __syncthreads();
+    const bool valid = k < count;
     const int i = first + k;
     const int M = fc.M;
     const bool use_sh = colors == nullptr;
-    float g16[16];
-    SurfelBwd o;
-    const bool vis = radii[i] > 0;
-    float* my_sh = use_sh ? d_sh + (size_t)3 * M * i : nullptr;
-    if (vis) {
-        const float4* row = reinterpret_cast<const float4*>(sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i);
+    if (valid) {
+        float g16[16];
+        SurfelBwd o;
+        const bool vis = radii[i] > 0;
+        float* my_sh = use_sh ? d_sh + (size_t)3 * M * i : nullptr;
+        float* row = s_sh + threadIdx.x * SH_PITCH;
+        if (vis) {
+            const float4* grow = reinterpret_cast<const float4*>(sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float4 v = __ldg(row + q);
-            g16[4 * q] = v.x; g16[4 * q + 1] = v.y; g16[4 * q + 2] = v.z; g16[4 * q + 3] = v.w;
-        }
-        const float* mean = means + (size_t)3 * i;
-        surfel_backward_geom(fc, mean, scales + (size_t)3 * i, rots + (size_t)4 * i, g.cov3D + (size_t)6 * i, g16, o);
-        if (use_sh) {
-            const float dir[3] = {mean[0] - fc.campos[0], mean[1] - fc.campos[1], mean[2] - fc.campos[2]};
-            const float gcol[3] = {g16[6], g16[7], g16[8]};
-            float add[3];
-            const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
-            const bool vec = ((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
-                             (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0;
-            float shreg[48], dsh[48];
-            const float* src = shs + (size_t)3 * M * i;
-            if (vec) {
+            for (int q = 0; q < 4; q++) {
+                const float4 v = __ldg(grow + q);
+                g16[4 * q] = v.x; g16[4 * q + 1] = v.y; g16[4 * q + 2] = v.z; g16[4 * q + 3] = v.w;
+            }
+            const float* mean = means + (size_t)3 * i;
+            surfel_backward_geom(fc, mean, scales + (size_t)3 * i, rots + (size_t)4 * i, g.cov3D + (size_t)6 * i, g16, o);
+            if (use_sh) {
+                const float dir[3] = {mean[0] - fc.campos[0], mean[1] - fc.campos[1], mean[2] - fc.campos[2]};
+                const float gcol[3] = {g16[6], g16[7], g16[8]};
+                float add[3];
+                if (SH_SMEM) {
+                    // in place: sh_backward finishes reading the row before its first store
+                    sh_backward(fc.D, row, dir, (uint32_t)g.clamped[i], gcol,
+                                [row](int kk, int ch, float v) { row[3 * kk + ch] = v; }, add);
+                    const int used = 3 * (fc.D + 1) * (fc.D + 1);
+                    for (int kk = used; kk < 48; kk++) row[kk] = 0.f; // coefficients above the active degree
+                } else {
+                    const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
+                    const bool vec = ((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                                     (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0;
+                    float shreg[48], dsh[48];
+                    const float* src = shs + (size_t)3 * M * i;
+                    if (vec) {
 #pragma unroll
-                for (int q = 0; q < 12; q++)
-                    if (4 * q < nfl) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
-                        shreg[4 * q] = v.x; shreg[4 * q + 1] = v.y; shreg[4 * q + 2] = v.z; shreg[4 * q + 3] = v.w;
+                        for (int q = 0; q < 12; q++)
+                            if (4 * q < nfl) {
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+                                shreg[4 * q] = v.x; shreg[4 * q + 1] = v.y; shreg[4 * q + 2] = v.z; shreg[4 * q + 3] = v.w;
+                            }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < 48; kk++)
+                            if (kk < nfl) shreg[kk] = __ldg(src + kk);
                     }
-            } else {
 #pragma unroll
-                for (int kk = 0; kk < 48; kk++)
-                    if (kk < nfl) shreg[kk] = __ldg(src + kk);
+                    for (int kk = 0; kk < 48; kk++) dsh[kk] = 0.f;
+                    sh_backward(fc.D, shreg, dir, (uint32_t)g.clamped[i], gcol,
+                                [&dsh](int kk, int ch, float v) { dsh[3 * kk + ch] = v; }, add);
+                    if (vec) {
+#pragma unroll
+                        for (int q = 0; q < 12; q++)
+                            if (4 * q < 3 * M)
+                                reinterpret_cast<float4*>(my_sh)[q] = make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]);
+                        for (int kk = 48; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < 48; kk++)
+                            if (kk < 3 * M) my_sh[kk] = dsh[kk];
+                        for (int kk = 48; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+                    }
+                }
+                o.d_mean[0] += add[0]; o.d_mean[1] += add[1]; o.d_mean[2] += add[2];
             }
+        } else {
 #pragma unroll
-            for (int kk = 0; kk < 48; kk++) dsh[kk] = 0.f;
-            sh_backward(fc.D, shreg, dir, (uint32_t)g.clamped[i], gcol,
-                        [&dsh](int kk, int ch, float v) { dsh[3 * kk + ch] = v; }, add);
-            if (vec) {
+            for (int q = 0; q < 16; q++) g16[q] = 0.f;
 #pragma unroll
-                for (int q = 0; q < 12; q++)
-                    if (4 * q < 3 * M)
-                        reinterpret_cast<float4*>(my_sh)[q] = make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]);
-                for (int kk = 48; kk < 3 * M; kk++) my_sh[kk] = 0.f;
-            } else {
+            for (int q = 0; q < 3; q++) { o.d_mean[q] = 0.f; o.d_scale[q] = 0.f; }
 #pragma unroll
-                for (int kk = 0; kk < 48; kk++)
-                    if (kk < 3 * M) my_sh[kk] = dsh[kk];
-                for (int kk = 48; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+            for (int q = 0; q < 4; q++) o.d_rot[q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 6; q++) o.d_cov3D[q] = 0.f;
+            if (use_sh) {
+                if (SH_SMEM) {
+                    for (int kk = 0; kk < 48; kk++) row[kk] = 0.f;
+                } else if (((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0) {
+                    for (int q = 0; 4 * q < 3 * M; q++) reinterpret_cast<float4*>(my_sh)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    for (int kk = 0; kk < 3 * M; kk++) my_sh[kk] = 0.f;
+                }
             }
-            o.d_mean[0] += add[0]; o.d_mean[1] += add[1]; o.d_mean[2] += add[2];
         }
-    } else {
+        d_means[3 * (size_t)i] = o.d_mean[0]; d_means[3 * (size_t)i + 1] = o.d_mean[1]; d_means[3 * (size_t)i + 2] = o.d_mean[2];
+        d_scales[3 * (size_t)i] = o.d_scale[0]; d_scales[3 * (size_t)i + 1] = o.d_scale[1]; d_scales[3 * (size_t)i + 2] = o.d_scale[2];
+        reinterpret_cast<float4*>(d_rots)[i] = make_float4(o.d_rot[0], o.d_rot[1], o.d_rot[2], o.d_rot[3]);
+        d_opacity[i] = g16[5];
+        if (d_means2D) { d_means2D[3 * (size_t)i] = g16[0]; d_means2D[3 * (size_t)i + 1] = g16[1]; d_means2D[3 * (size_t)i + 2] = 0.f; }
+        if (d_colors) { d_colors[3 * (size_t)i] = g16[6]; d_colors[3 * (size_t)i + 1] = g16[7]; d_colors[3 * (size_t)i + 2] = g16[8]; }
+        if (d_cov3D) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) g16[q] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 3; q++) { o.d_mean[q] = 0.f; o.d_scale[q] = 0.f; }
-#pragma unroll
-        for (int q = 0; q < 4; q++) o.d_rot[q] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 6; q++) o.d_cov3D[q] = 0.f;
-        if (use_sh) {
-            if (((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0) {
-                for (int q = 0; 4 * q < 3 * M; q++) reinterpret_cast<float4*>(my_sh)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int kk = 0; kk < 3 * M; kk++) my_sh[kk] = 0.f;
-            }
+            for (int q = 0; q < 6; q++) d_cov3D[6 * (size_t)i + q] = o.d_cov3D[q];
         }
     }
-    d_means[3 * (size_t)i] = o.d_mean[0]; d_means[3 * (size_t)i + 1] = o.d_mean[1]; d_means[3 * (size_t)i + 2] = o.d_mean[2];
-    d_scales[3 * (size_t)i] = o.d_scale[0]; d_scales[3 * (size_t)i + 1] = o.d_scale[1]; d_scales[3 * (size_t)i + 2] = o.d_scale[2];
-    reinterpret_cast<float4*>(d_rots)[i] = make_float4(o.d_rot[0], o.d_rot[1], o.d_rot[2], o.d_rot[3]);
-    d_opacity[i] = g16[5];
-    if (d_means2D) { d_means2D[3 * (size_t)i] = g16[0]; d_means2D[3 * (size_t)i + 1] = g16[1]; d_means2D[3 * (size_t)i + 2] = 0.f; }
-    if (d_colors) { d_colors[3 * (size_t)i] = g16[6]; d_colors[3 * (size_t)i + 1] = g16[7]; d_colors[3 * (size_t)i + 2] = g16[8]; }
-    if (d_cov3D) {
-#pragma unroll
-        for (int q = 0; q < 6; q++) d_cov3D[6 * (size_t)i + q] = o.d_cov3D[q];
+    if (SH_SMEM) {
+        __syncthreads();
+        unstage_sh_rows(s_sh, d_sh + (size_t)48 * row0, rows); // coalesced 16-byte stores of the CTA's dL/dSH block
     }
 }
 
@@ -194,8 +245,14 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
                                   GeomView g, ImgView im, int32_t* radii, uint8_t* active, cudaStream_t s) {
     const int P = f.num_surfels;
     if (P == 0) return cudaSuccess;
-    k_surfel_forward<<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im, radii,
-                                                     active);
+    // staged-SH fast path: SH colours with exactly 16 coefficients per surfel and 16-byte aligned rows
+    const bool sh_smem = colors == nullptr && f.sh_coeffs == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
+    if (sh_smem)
+        k_surfel_forward<true><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
+                                                               radii, active);
+    else
+        k_surfel_forward<false><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
+                                                                im, radii, active);
     return cudaGetLastError();
 }
 
@@ -205,9 +262,16 @@ cudaError_t launch_surfel_backward(const egs_frame& f, int first, int count, con
                                    float* d_scales, float* d_rots, float* d_means2D, float* d_colors, float* d_cov3D,
                                    cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
-    k_surfel_backward<<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots, radii, g,
-                                                          sg, d_means, d_opacity, d_sh, d_scales, d_rots, d_means2D,
-                                                          d_colors, d_cov3D);
+    const bool sh_smem = colors == nullptr && f.sh_coeffs == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0;
+    if (sh_smem)
+        k_surfel_backward<true><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
+                                                                    radii, g, sg, d_means, d_opacity, d_sh, d_scales,
+                                                                    d_rots, d_means2D, d_colors, d_cov3D);
+    else
+        k_surfel_backward<false><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
+                                                                     radii, g, sg, d_means, d_opacity, d_sh, d_scales,
+                                                                     d_rots, d_means2D, d_colors, d_cov3D);
     return cudaGetLastError();
 }
 

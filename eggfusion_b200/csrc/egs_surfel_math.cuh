@@ -293,6 +293,7 @@ EGS_HD void dnormalize3(const float v[3], const float dv[3], float out[3]) {
 }
 
 // SH backward: writes d_sh[0 .. (deg+1)^2) x 3 through `store(k, ch, value)` and returns dL/d(direction).
+// All reads of `sh` happen before the first `store`, so the output may alias the input.
 template <class Store>
 EGS_HD void sh_backward(int deg, const float* sh, const float dir_orig[3], uint32_t clamped, const float g_in[3],
                         Store store, float d_mean_add[3]) {
@@ -310,29 +311,10 @@ EGS_HD void sh_backward(int deg, const float* sh, const float dir_orig[3], uint3
         store(k, 1, cf * g[1]);                       \
         store(k, 2, cf * g[2]);                       \
     }
-    OUT_(0, EGS_SH_C0);
+    // 1. dL/d(direction): reads every coefficient.  Done first so that `store` may overwrite `sh` in place.
+    float xx = 0, yy = 0, zz = 0, xy = 0, yz = 0, xz = 0;
+    if (deg > 1) { xx = x * x; yy = y * y; zz = z * z; xy = x * y; yz = y * z; xz = x * z; }
     if (deg > 0) {
-        OUT_(1, -EGS_SH_C1 * y);
-        OUT_(2, EGS_SH_C1 * z);
-        OUT_(3, -EGS_SH_C1 * x);
-        float xx = 0, yy = 0, zz = 0, xy = 0, yz = 0, xz = 0;
-        if (deg > 1) {
-            xx = x * x; yy = y * y; zz = z * z; xy = x * y; yz = y * z; xz = x * z;
-            OUT_(4, EGS_SH_C2_0 * xy);
-            OUT_(5, EGS_SH_C2_1 * yz);
-            OUT_(6, EGS_SH_C2_2 * (2.f * zz - xx - yy));
-            OUT_(7, EGS_SH_C2_3 * xz);
-            OUT_(8, EGS_SH_C2_4 * (xx - yy));
-            if (deg > 2) {
-                OUT_(9, EGS_SH_C3_0 * y * (3.f * xx - yy));
-                OUT_(10, EGS_SH_C3_1 * xy * z);
-                OUT_(11, EGS_SH_C3_2 * y * (4.f * zz - xx - yy));
-                OUT_(12, EGS_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                OUT_(13, EGS_SH_C3_4 * x * (4.f * zz - xx - yy));
-                OUT_(14, EGS_SH_C3_5 * z * (xx - yy));
-                OUT_(15, EGS_SH_C3_6 * x * (xx - 3.f * yy));
-            }
-        }
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
             float dx = -EGS_SH_C1 * S_(3, ch), dy = -EGS_SH_C1 * S_(1, ch), dz = EGS_SH_C1 * S_(2, ch);
@@ -359,6 +341,29 @@ EGS_HD void sh_backward(int deg, const float* sh, const float dir_orig[3], uint3
             ddx += dx * g[ch];
             ddy += dy * g[ch];
             ddz += dz * g[ch];
+        }
+    }
+    // 2. dL/dSH = basis * dL/dRGB
+    OUT_(0, EGS_SH_C0);
+    if (deg > 0) {
+        OUT_(1, -EGS_SH_C1 * y);
+        OUT_(2, EGS_SH_C1 * z);
+        OUT_(3, -EGS_SH_C1 * x);
+        if (deg > 1) {
+            OUT_(4, EGS_SH_C2_0 * xy);
+            OUT_(5, EGS_SH_C2_1 * yz);
+            OUT_(6, EGS_SH_C2_2 * (2.f * zz - xx - yy));
+            OUT_(7, EGS_SH_C2_3 * xz);
+            OUT_(8, EGS_SH_C2_4 * (xx - yy));
+            if (deg > 2) {
+                OUT_(9, EGS_SH_C3_0 * y * (3.f * xx - yy));
+                OUT_(10, EGS_SH_C3_1 * xy * z);
+                OUT_(11, EGS_SH_C3_2 * y * (4.f * zz - xx - yy));
+                OUT_(12, EGS_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
+                OUT_(13, EGS_SH_C3_4 * x * (4.f * zz - xx - yy));
+                OUT_(14, EGS_SH_C3_5 * z * (xx - yy));
+                OUT_(15, EGS_SH_C3_6 * x * (xx - 3.f * yy));
+            }
         }
     }
 #undef S_
