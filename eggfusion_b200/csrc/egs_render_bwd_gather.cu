@@ -10,6 +10,9 @@
 //            a per-warp table and accumulating the 14 sums in registers -- plain FP32 FMAs, all 32 lanes busy, no
 //            selects.  Two shuffle steps merge the four quarters, and each of the four lanes of a splat issues one
 //            16-byte vector reduction (red.global.add.v4.f32) of its quad of G[surfel][16].
+//            Splats still parked when a staging buffer is about to be recycled have the three record words phase 2
+//            needs copied into the padding units of their row, so phase 2 always runs on a full set of 8 (except
+//            once, at the end of the tile) instead of being flushed half-empty after every batch.
 // ~35 issue slots per (warp, splat) for the reduction, no CTA-wide combine pass and no per-batch barriers for it.
 // Record staging is double-buffered with cp.async (LDGSTS): while a batch is walked, the next batch's 64-byte
 // records and blend masks stream into the other buffer and the surfel ids of the batch after that are already in
@@ -54,7 +57,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 struct GatherSmem {
     float4 rec[2][GB_BATCH * 4];
     uint32_t lm[2][GB_BATCH * 8];
-    uint32_t id[2][GB_BATCH];
     float4 pair[GB_WARPS][GB_PEND * GB_ROW];
     float4 ktab[GB_WARPS][32 * 2];
     int top;
@@ -121,12 +123,12 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
     float T = T_final;
     float sigma = 0.f;
     uint32_t rec_base = smem_addr(S.rec[0]);
-    const uint32_t* cur_id = S.id[0];
     const uint32_t* cur_lm = S.lm[0];
     const uint32_t pair_base = smem_addr(S.pair[warp]);
     const uint32_t ktab_base = smem_addr(S.ktab[warp]);
     const int h = lane >> 2, p = lane & 3;
-    int npend = 0, myj = 0;
+    int npend = 0;
+    uint32_t myrec = 0;   // shared address of the record (q0..q2; surfel id in q0.z) of parked splat h
     // phase-2 pixel coordinates: lane (h, p) visits pixels k = 4 i + p, i.e. block column p + 4 (i & 1), row i >> 1
     const float fpx0 = (float)(bx + p), fpy0 = (float)by;
 
@@ -138,7 +140,7 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
         for (int i = 0; i < 14; i++) a[i] = 0.f;
         float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (h < np) {
-            q0 = lds128(rec_base + 64u * (uint32_t)myj);
+            q0 = lds128(myrec);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int k = 4 * i + p; // pixel (lane index of phase 1)
@@ -165,10 +167,10 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
             a[i] += __shfl_xor_sync(0xffffffffu, a[i], 2);
         }
         if (h < np) {
-            float* dst = sg + (size_t)EGS_SCREEN_GRAD_STRIDE * cur_id[myj] + 4 * p;
+            float* dst = sg + (size_t)EGS_SCREEN_GRAD_STRIDE * __float_as_uint(q0.z) + 4 * p;
             if (p == 0) {
-                const float4 q1 = lds128(rec_base + 64u * (uint32_t)myj + 16u);
-                const float4 q2 = lds128(rec_base + 64u * (uint32_t)myj + 32u);
+                const float4 q1 = lds128(myrec + 16u);
+                const float4 q2 = lds128(myrec + 32u);
                 const float v0 = kx * (q1.x * a[0] + q1.y * a[1]) - q2.x * a[2];   // backward.cu:648-660
                 const float v1 = ky * (q1.z * a[1] + q1.y * a[0]) - q2.y * a[2];
                 red_add_v4_g(dst, v0, v1, a[3], a[4]);
@@ -188,7 +190,6 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
     const int tid = threadIdx.x;
     auto stage = [&](int buf, int top_b, uint32_t idv) {   // threads tid < GB_BATCH
         if (tid < min(GB_BATCH, top_b)) {
-            S.id[buf][tid] = idv;
             const float4* src = reinterpret_cast<const float4*>(rec + idv);
 #pragma unroll
             for (int q = 0; q < 4; q++) cp_async16(&S.rec[buf][tid * 4 + q], src + q);
@@ -201,10 +202,11 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
         }
     };
     const int nb = (top0 + GB_BATCH - 1) / GB_BATCH;
-    uint32_t next_id = 0;
+    uint32_t next_id = 0, staged_id = 0;
     if (tid < GB_BATCH && nb > 0) {
         if (tid < min(GB_BATCH, top0)) next_id = __ldg(plist + (top0 - 1 - tid));
         stage(0, top0, next_id);
+        staged_id = next_id;
         const int top1 = top0 - GB_BATCH;
         if (nb > 1 && tid < min(GB_BATCH, top1)) next_id = __ldg(plist + (top1 - 1 - tid));
     }
@@ -213,16 +215,18 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
     for (int b = 0; b < nb; b++) {
         const int buf = b & 1;
         cp_async_wait_all();
+        // the extent word of the record (forward-only) is replaced by the surfel id: phase 2 finds it there
+        if (tid < GB_BATCH) reinterpret_cast<uint32_t*>(&S.rec[buf][tid * 4])[2] = staged_id;
         __syncthreads(); // batch b has landed; every warp is done with batch b-1 (whose buffer is refilled next)
         if (tid < GB_BATCH) {
             const int top_n = top0 - (b + 1) * GB_BATCH;
             if (b + 1 < nb) stage(buf ^ 1, top_n, next_id);
+            staged_id = next_id;
             const int top_nn = top_n - GB_BATCH;
             if (b + 2 < nb && tid < min(GB_BATCH, top_nn)) next_id = __ldg(plist + (top_nn - 1 - tid));
         }
         cp_async_commit();
         rec_base = smem_addr(S.rec[buf]);
-        cur_id = S.id[buf];
         cur_lm = S.lm[buf];
 
 #pragma unroll 1
@@ -257,13 +261,23 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
                     u = G * dL_dalpha;
                 }
                 sts128(pair_base + 16u * (uint32_t)(npend * GB_ROW + lane), w, dd, u, act ? 1.f : 0.f);
-                if (h == npend) myj = j;
+                if (h == npend) myrec = rad;
                 if (++npend == GB_PEND) { reduce_pending(GB_PEND); npend = 0; }
             }
         }
-        // the staging buffers (records, ids) of this batch are needed by phase 2: flush before they are overwritten
-        if (npend) { reduce_pending(npend); npend = 0; }
+        // Splats still parked point into this batch's staging buffer, which is refilled during the batch after
+        // next: move their q0..q2 into the padding units 32..34 of their row (lane p copies unit p).
+        if (h < npend) {
+            const uint32_t keep = pair_base + 16u * (uint32_t)(h * GB_ROW + 32);
+            if (p < 3) {
+                const float4 v = lds128(myrec + 16u * (uint32_t)p);
+                sts128(keep + 16u * (uint32_t)p, v.x, v.y, v.z, v.w);
+            }
+            myrec = keep;
+        }
+        __syncwarp();
     }
+    if (npend) reduce_pending(npend);
 }
 
 cudaError_t launch_render_backward_gather(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,

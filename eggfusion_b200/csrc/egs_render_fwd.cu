@@ -74,6 +74,8 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
     const float tile_x0 = (float)(tx * EGS_TILE), tile_y0 = (float)(ty * EGS_TILE);
 
     const uint32_t rec_base = smem_addr(s_rec);
+    const uint32_t wm_lane = smem_addr(s_wm) + 4u * (uint32_t)lane;    // this lane's slot of a 32-entry chunk
+    const uint32_t lm_warp = smem_addr(s_lm) + 4u * (uint32_t)warp;    // this warp's word of an entry's mask row
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f;
     uint32_t last = 0;
     bool done = !inside;
@@ -97,7 +99,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
         if (!__all_sync(0xffffffffu, done)) {
             const int chunks = (m + 31) >> 5;
             for (int c = 0; c < chunks; c++) {
-                unsigned hits = __ballot_sync(0xffffffffu, (s_wm[c * 32 + lane] >> warp) & 1u);
+                unsigned hits = __ballot_sync(0xffffffffu, (lds32(wm_lane + 128u * (uint32_t)c) >> warp) & 1u);
                 while (hits) {
                     const int j = c * 32 + __ffs(hits) - 1;
                     hits &= hits - 1;
@@ -112,7 +114,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                     if (ok && test_T < 0.0001f) { done = true; ok = false; }   // stops WITHOUT blending this one
                     const unsigned bm = __ballot_sync(0xffffffffu, ok);
                     if (bm == 0u) continue;
-                    if (lane == 0) s_lm[8 * j + warp] = bm;
+                    sts32(lm_warp + 32u * (uint32_t)j, bm);   // every lane stores the same word: one wavefront
                     if (ok) {
                         const float w = __fmul_rn(alpha, T);
                         const float4 q2 = lds128(ra + 32u), q3 = lds128(ra + 48u);
