@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeggsplat.so")
+# EGS_LIB: developer hook for A/B runs of alternative builds of the same library (profiles/ab_variants.sh)
+LIB_PATH = os.environ.get("EGS_LIB") or os.path.join(_HERE, "libeggsplat.so")
 CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 

@@ -245,6 +245,9 @@ k_render_backward(int W, int H, int gx, const float* __restrict__ bg, const Spla
 cudaError_t launch_render_backward_mma(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
                                        const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                        cudaStream_t s);
+cudaError_t launch_render_backward_warp(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
+                                        const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
+                                        cudaStream_t s);
 cudaError_t launch_render_backward_gather(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
                                           const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                           cudaStream_t s);
@@ -258,7 +261,7 @@ static int bwd_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("EGS_BWD_KERNEL");
-        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : 2;
+        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : (e && e[0] == 'w') ? 3 : 2;
     }
     return v;
 }
@@ -267,6 +270,7 @@ cudaError_t launch_render_backward(const egs_frame& f, GeomView g, ImgView im, B
                                    const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                    cudaStream_t s) {
     if (bwd_variant() == 1) return launch_render_backward_mma(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
+    if (bwd_variant() == 3) return launch_render_backward_warp(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
     if (bwd_variant() == 2) return launch_render_backward_gather(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
     const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
     k_render_backward<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, gC, gN, gD,

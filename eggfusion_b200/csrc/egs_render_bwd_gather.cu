@@ -19,7 +19,12 @@
 // registers, so a tile pays the dependent-gather latency once instead of once per batch.
 #include "egs_common.cuh"
 
+#ifndef GB_BATCH
 #define GB_BATCH 32
+#endif
+#ifndef GB_MINCTAS
+#define GB_MINCTAS 4
+#endif
 #define GB_WARPS (EGS_TILE_THREADS / 32)
 #define GB_PEND 8          // splats parked per warp before a phase-2 pass
 #define GB_ROW 36          // float4 units per parked splat row (32 pixels + padding: conflict-free both ways)
@@ -63,7 +68,7 @@ struct GatherSmem {
 };
 } // namespace
 
-__global__ void __launch_bounds__(EGS_TILE_THREADS, 4)
+__global__ void __launch_bounds__(EGS_TILE_THREADS, GB_MINCTAS)
 k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec,
                          ImgView im, BinView bn, long long cap, const float* __restrict__ gC,
                          const float* __restrict__ gN, const float* __restrict__ gDp, const float* __restrict__ gOp,
@@ -230,9 +235,9 @@ k_render_backward_gather(int W, int H, int gx, const float* __restrict__ bg, con
         cur_lm = S.lm[buf];
 
 #pragma unroll 1
-        for (int c = 0; c < GB_BATCH / 32; c++) {
+        for (int c = 0; c < (GB_BATCH + 31) / 32; c++) {
             const int jl = c * 32 + lane;
-            unsigned hits = __ballot_sync(0xffffffffu, cur_lm[8 * jl + warp] != 0u);
+            unsigned hits = __ballot_sync(0xffffffffu, (GB_BATCH % 32 == 0 || jl < GB_BATCH) && cur_lm[8 * jl + warp] != 0u);
             while (hits) {
                 const int j = c * 32 + __ffs(hits) - 1; // batch entry j = list position top-1-j (back to front)
                 hits &= hits - 1;

@@ -326,17 +326,19 @@ def test_backward_kernel_variants_agree():
         "np.save(sys.argv[1], o['g_screen'])\n"
     ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
     outs = {}
-    for variant in ("butterfly", "mma", "gather"):
+    for variant in ("butterfly", "mma", "gather", "warp"):
         path = "/tmp/egs_variant_%s.npy" % variant
         env = dict(os.environ, EGS_BWD_KERNEL=variant)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=util.ROOT)
         outs[variant] = np.load(path)
     assert rel_err(outs["mma"], outs["butterfly"]) <= 2e-5
     assert rel_err(outs["gather"], outs["butterfly"]) <= 2e-5
+    assert rel_err(outs["warp"], outs["butterfly"]) <= 2e-5
     cam, sc, g, bg, mask, deg, f, b = util.oracle_run("c1_posed_bg")
     sg = util.screen_block_from_oracle(b, sc["xyz"].shape[0])
     assert rel_err(outs["mma"], sg) <= TOL
     assert rel_err(outs["gather"], sg) <= TOL
+    assert rel_err(outs["warp"], sg) <= TOL
 
 
 def _random_case(seed, P, W, H, deg, layers=3, big=False, dense_tile=False):
