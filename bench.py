@@ -362,7 +362,7 @@ def run_ours(args):
     else:
         dom_kernel, dom_bytes = "k_" + kern_of[dom_stage], ab[kern_of[dom_stage]]
         if dom_stage == "bwd_render":
-            dom_kernel = "k_render_backward_" + os.environ.get("EGS_BWD_KERNEL", "gather")
+            dom_kernel = "k_render_backward_" + os.environ.get("EGS_BWD_KERNEL", "warp")
     achieved = dom_bytes / (stage_ms[dom_stage] * 1e-3) / 1e9
     traffic = None
     try:  # DRAM bytes of the same kernel from the committed ncu capture of this workload (profiles/)

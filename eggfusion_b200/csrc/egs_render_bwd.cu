@@ -252,16 +252,19 @@ cudaError_t launch_render_backward_gather(const egs_frame& f, GeomView g, ImgVie
                                           const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                           cudaStream_t s);
 
-// Three implementations of the same walk, selected with EGS_BWD_KERNEL (default: gather).  Measured on B200 at C3:
-//   gather     transposed FP32 reduction + cp.async double-buffered staging (egs_render_bwd_gather.cu)   1.15 ms
+// Four implementations of the same walk, selected with EGS_BWD_KERNEL (default: warp).  Measured on B200 at C3:
+//   warp       one 8x4 block per 32-thread CTA, per-warp compacted staging, no CTA barriers
+//              (egs_render_bwd_warp.cu)                                                                  1.00 ms
+//   gather     one tile per CTA, transposed FP32 reduction + cp.async double-buffered staging
+//              (egs_render_bwd_gather.cu)                                                                1.04 ms
 //   butterfly  16-shuffle transposing butterfly + shared-memory combine (this file)                      1.38 ms
 //   mma        cross-pixel sums on the tensor cores, mma.sync 3xTF32 (egs_render_bwd_mma.cu)             1.62 ms
-// The legacy mma.sync path costs more issue slots than it saves here.  All three are covered by the parity tests.
+// The legacy mma.sync path costs more issue slots than it saves here.  All four are covered by the parity tests.
 static int bwd_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("EGS_BWD_KERNEL");
-        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : (e && e[0] == 'w') ? 3 : 2;
+        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : (e && e[0] == 'g') ? 2 : 3;   // default: warp
     }
     return v;
 }
