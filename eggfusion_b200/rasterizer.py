@@ -69,8 +69,15 @@ class _Config:
     "exact": read the instance count back after the per-surfel stage (one 16-byte D2H + stream sync per forward;
              the reference needs two blocking copies plus a host loop, rasterizer_impl.cu:311,349-366).
     int    : fixed capacity in instances, no host sync at all; an overflow raises at the next forward/backward.
+    "auto" : "exact" the first time a (surfel count, image size) is seen, afterwards `auto_headroom` x (+ `auto_slack`) the largest
+             instance count reported by the last `auto_window` forwards of that shape -- no host sync in steady state
+             (an optimisation loop's instance count drifts slowly).  Counts come back asynchronously; an overflow
+             raises at the next forward/backward like the fixed capacity does.
     """
     capacity = "exact"
+    auto_headroom = 1.5
+    auto_slack = 4096       # instances added on top of the head-room (small scenes fluctuate relatively more)
+    auto_window = 8
 
 
 config = _Config()
@@ -82,14 +89,25 @@ def _get_pinned():
     return _pinned_free.pop() if _pinned_free else torch.empty((4,), dtype=torch.int32).pin_memory()
 
 
+_auto_history = {}      # (device index, P, W, H) -> recent instance counts ("auto" capacity)
+
+
+def _auto_note(key, count: int):
+    h = _auto_history.setdefault(key, [])
+    h.append(int(count))
+    del h[:-config.auto_window]
+
+
 def _check_pending(block: bool = False):
     while _pending_overflow:
-        ev, host, cap = _pending_overflow[0]
+        ev, host, cap, key = _pending_overflow[0]
         if not block and not ev.query():
             return
         ev.synchronize()
         _pending_overflow.pop(0)
         _pinned_free.append(host)
+        if key is not None:
+            _auto_note(key, int(host[0]))
         if int(host[2]) != 0:
             raise RuntimeError(
                 f"eggsplat: a previous forward produced {int(host[0])} instances but the binning workspace was sized "
@@ -165,6 +183,11 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
         st.img = torch.empty((ib,), **u8)
 
         capacity = config.capacity if capacity is None else capacity
+        auto_key = None
+        if capacity == "auto":
+            auto_key = (device.index, P, W, H)
+            hist = _auto_history.get(auto_key)
+            capacity = "exact" if not hist else int(max(hist) * config.auto_headroom) + config.auto_slack
         exact = capacity == "exact"
         host = _get_pinned()
         _lib.check(lib.egs_forward_plan(C.byref(frame), _ptr(means3D), _ptr(shs) if use_sh else None,
@@ -177,6 +200,8 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
             st.num_rendered, st.tile_num = int(host[0]), int(host[1])
             st.cap = st.num_rendered
             _pinned_free.append(host)
+            if auto_key is not None:
+                _auto_note(auto_key, st.num_rendered)
         else:
             st.cap = int(capacity)
             st.num_rendered = st.tile_num = -1  # unknown on the host by design
@@ -189,7 +214,7 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
         if not exact:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
-            _pending_overflow.append((ev, host, st.cap))
+            _pending_overflow.append((ev, host, st.cap, auto_key))
     return color, normal, depth, opac, active, radii, st
 
 

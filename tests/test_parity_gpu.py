@@ -255,6 +255,34 @@ def test_fixed_capacity_mode_and_overflow_detection():
         R._check_pending(block=True)
 
 
+def test_auto_capacity_policy():
+    """"auto": exact on the first forward of a shape, then history-sized without a host sync; same results."""
+    from eggfusion_b200 import rasterizer as R
+    name = "small_deg2"
+    exact = cuda_run(name)
+    R._auto_history.clear()
+    first = cuda_run(name, capacity="auto")       # no history yet: behaves like "exact"
+    assert first["num_rendered"] == exact["num_rendered"]
+    again = cuda_run(name, capacity="auto")       # sized from the history, instance count unknown on the host
+    assert again["num_rendered"] == -1
+    assert np.array_equal(again["color"], exact["color"])
+    assert np.array_equal(again["point_list"][:exact["num_rendered"]], exact["point_list"])
+    assert rel_err(again["g_means3D"], first["g_means3D"]) <= 1e-5   # float reductions are order-dependent
+    R._check_pending(block=True)
+    key = next(iter(R._auto_history))
+    assert R._auto_history[key][-1] == exact["num_rendered"]
+    # a history that undershoots (scene grew by more than the headroom) is reported, not silently truncated
+    R._auto_history[key] = [max(1, exact["num_rendered"] // 4)]
+    slack, R.config.auto_slack = R.config.auto_slack, 0
+    try:
+        cuda_run(name, capacity="auto")
+        with pytest.raises(RuntimeError, match="truncated"):
+            R._check_pending(block=True)
+    finally:
+        R.config.auto_slack = slack
+        R._auto_history.clear()
+
+
 def test_mark_visible_matches_oracle():
     import eggfusion_b200 as E
     from oracle import oracle as orc
