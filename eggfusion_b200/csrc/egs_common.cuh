@@ -4,9 +4,13 @@
 //   geom workspace, per surfel:   SplatRecord rec[P] (64 B, 16-B aligned quads) | cov3D[P][6] f32 |
 //                                 tiles_touched[P] u32 | clamped[P] u8
 //   img  workspace:               egs_counters (+ticket) | tile_count[T] | tile_offset[T+1] | tile_cursor[T] |
-//                                 tile_list[T] (compacted non-empty tiles) | final_T[N] | final_D[N] | n_contrib[N]
+//                                 tile_list[T] (compacted non-empty tiles) | hit_count[8T] | final_T[N] | final_D[N] |
+//                                 n_contrib[N]
 //   bin  workspace, per instance: keys[cap] u64 (depth bits << 32 | surfel id, bucketed by tile) | point_list[cap] u32 |
-//                                 lane_masks[cap][8] u32 (which pixels of each 8x4 warp block blended the instance)
+//                                 hits[8*cap] {surfel id, pixel mask}: per (tile, 8x4 warp block) the compacted, depth-
+//                                 ordered list of splats that blended into the block (block b of a tile whose list is
+//                                 [start, start+n) owns entries 8*start + b*n ...); the tile-wide backward variants
+//                                 use the same bytes as lane_masks[cap][8] u32 instead
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -92,6 +96,7 @@ struct ImgView {
     uint32_t* tile_offset; // [T + 1]
     uint32_t* tile_cursor;
     int32_t* tile_list;    // [T]
+    uint32_t* hit_count;   // [8T] entries of each (tile, warp block) hit list
     float* final_T;
     float* final_D;
     uint32_t* n_contrib;
@@ -101,6 +106,7 @@ struct BinView {
     unsigned long long* keys;
     uint32_t* point_list;
     uint32_t* lane_masks; // [cap][8]: bit l of word w = pixel l of warp block w blended this instance in the forward
+    uint2* hits;          // [8*cap] (aliases lane_masks): per-block hit lists {surfel id, mask of the block's pixels}
     size_t bytes;
 };
 
@@ -125,6 +131,7 @@ EGS_HD ImgView carve_img(void* base, size_t tiles, size_t npix) {
     v.tile_offset = (uint32_t*)(b + o);     o = egs_align_up(o + 4 * (tiles + 1), 256);
     v.tile_cursor = (uint32_t*)(b + o);     o = egs_align_up(o + 4 * tiles, 256);
     v.tile_list = (int32_t*)(b + o);        o = egs_align_up(o + 4 * tiles, 256);
+    v.hit_count = (uint32_t*)(b + o);       o = egs_align_up(o + 32 * tiles, 256);
     v.final_T = (float*)(b + o);            o = egs_align_up(o + 4 * npix, 256);
     v.final_D = (float*)(b + o);            o = egs_align_up(o + 4 * npix, 256);
     v.n_contrib = (uint32_t*)(b + o);       o = egs_align_up(o + 4 * npix, 256);
@@ -137,7 +144,8 @@ EGS_HD BinView carve_bin(void* base, size_t cap) {
     char* b = (char*)base;
     v.keys = (unsigned long long*)(b + o);  o = egs_align_up(o + 8 * cap, 256);
     v.point_list = (uint32_t*)(b + o);      o = egs_align_up(o + 4 * cap, 256);
-    v.lane_masks = (uint32_t*)(b + o);      o = egs_align_up(o + 32 * cap, 256);
+    v.lane_masks = (uint32_t*)(b + o);
+    v.hits = (uint2*)(b + o);               o = egs_align_up(o + 64 * cap, 256);
     v.bytes = o + 256;
     return v;
 }
@@ -151,6 +159,10 @@ EGS_HD void egs_tile_rect(float px, float py, int radius, int gx, int gy, int& x
     a = (int)f_mul(f_sub(f_add(f_add(px, r), 16.0f), 1.0f), 0.0625f);        x1 = a < 0 ? 0 : (a > gx ? gx : a);
     a = (int)f_mul(f_sub(f_add(f_add(py, r), 16.0f), 1.0f), 0.0625f);        y1 = a < 0 ? 0 : (a > gy ? gy : a);
 }
+
+// Which reverse-walk kernel runs (EGS_BWD_KERNEL, see egs_render_bwd.cu): 3 = warp (default, consumes per-block hit
+// lists), 0/1/2 = tile-wide variants (consume lane_masks).  The forward writes the format the backward will read.
+int egs_bwd_variant();
 
 #if defined(__CUDACC__)
 // 16-byte shared-memory load from a 32-bit shared-window address.  Indexing __shared__ arrays through generic

@@ -7,11 +7,11 @@
 // batch although their work differs (a splat touches 2.7 of the 8 blocks on average, unevenly): ncu showed
 // 36 % of the stall samples on that barrier.  Here every 8x4 block is its own 32-thread CTA:
 //   * no CTA-wide barriers at all (only __syncwarp), no tile tail that keeps seven finished warps resident;
-//   * a warp stages ONLY the splats that blended into its block: per 32 list entries it reads its word of the saved
-//     blend masks, compacts the hits with a ballot, and cp.async-copies just those 64-byte records into its own
-//     double buffer (the next chunk's records and the masks / ids of the chunk after that are in flight while the
-//     current chunk is walked);
-//   * the walk stops at the warp's own last contributor instead of the tile-wide one.
+//   * a warp stages ONLY the splats that blended into its block: the forward left it a compacted, depth-ordered
+//     hit list {surfel id, pixel mask} (egs_render_fwd.cu, HITLIST), so a chunk is 32 coalesced 8-byte entries, all
+//     of them real hits, whose 64-byte records are cp.async-copied into the warp's own double buffer (the next
+//     chunk's records and the entries of the chunk after that are in flight while the current chunk is walked);
+//   * the walk covers exactly the block's own contributors, back to front.
 // Shared memory is 10 KB per warp, so 20 warps are resident per SM, all of them runnable.
 #include "egs_common.cuh"
 
@@ -79,12 +79,7 @@ k_render_backward_warp(int W, int H, int gx, const float* __restrict__ bg, const
     const size_t pix = (size_t)W * py + px;
     const float pxf = (float)px, pyf = (float)py;
 
-    int last_contributor = 0;
-    if (inside) last_contributor = (int)im.n_contrib[pix];
-    int top = last_contributor;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) top = max(top, __shfl_xor_sync(full, top, d));
-    top = min(top, n);
+    const int top = (int)min(im.hit_count[blockIdx.x], (uint32_t)n);   // entries of this block's hit list
     if (top <= 0) return;   // nothing was blended into this block
 
     float T_final = 0.f, D_final = 0.f;
@@ -98,28 +93,27 @@ k_render_backward_warp(int W, int H, int gx, const float* __restrict__ bg, const
         gO = __ldg(gOp + pix);
     }
 
-    const uint32_t* __restrict__ plist = bn.point_list + start;
-    const uint32_t* __restrict__ lmw = bn.lane_masks + 8 * (size_t)start + blk;   // this block's word, stride 8
+    const uint2* __restrict__ hseg = bn.hits + 8 * (size_t)start + (size_t)blk * (size_t)n;
     const int nc = (top + 31) >> 5;
-    // chunk c covers list positions top-1-32c ... top-32(c+1) (back to front); lane l holds position top-1-(32c+l)
+    // chunk c covers hit-list positions top-1-32c ... top-32(c+1) (back to front); lane l holds position top-1-(32c+l)
     auto load_chunk = [&](int c, uint32_t& m, uint32_t& idv) {
         const int pos = top - 1 - (32 * c + lane);
         m = 0u;
         idv = 0u;
-        if (c < nc && pos >= 0) {
-            m = __ldg(lmw + 8 * (size_t)pos);
-            idv = __ldg(plist + pos);
+        if (pos >= 0) {
+            const uint2 e = __ldg(hseg + pos);
+            idv = e.x;
+            m = e.y;
         }
     };
     const uint32_t rec_smem = smem_addr(S.rec);
     const uint32_t lm_smem = smem_addr(S.lm);
     const uint32_t id_smem = smem_addr(S.id);
     // compact the chunk's hits into staging buffer `buf`; returns their count
-    auto stage_chunk = [&](int buf, uint32_t m, uint32_t idv) -> int {
-        const unsigned hb = __ballot_sync(full, m != 0u);
+    // (every entry of a hit list has a non-empty mask, so a chunk is dense: slot = lane)
+    auto stage_chunk = [&](int c, int buf, uint32_t m, uint32_t idv) -> int {
         if (m != 0u) {
-            const uint32_t r = (uint32_t)__popc(hb & ((1u << lane) - 1u));
-            const uint32_t slot = (uint32_t)buf * 32u + r;
+            const uint32_t slot = (uint32_t)buf * 32u + (uint32_t)lane;
             sts32(lm_smem + 4u * slot, m);
             sts32(id_smem + 4u * slot, idv);
             const float4* src = reinterpret_cast<const float4*>(rec + idv);
@@ -127,12 +121,12 @@ k_render_backward_warp(int W, int H, int gx, const float* __restrict__ bg, const
 #pragma unroll
             for (int q = 0; q < 4; q++) cp_async16_w(dst + 16u * q, src + q);
         }
-        return __popc(hb);
+        return min(32, top - 32 * c);
     };
 
     uint32_t mA, idA;
     load_chunk(0, mA, idA);
-    int cnt_cur = stage_chunk(0, mA, idA);
+    int cnt_cur = stage_chunk(0, 0, mA, idA);
     cp_async_commit_w();
     load_chunk(1, mA, idA);
 
@@ -239,7 +233,7 @@ k_render_backward_warp(int W, int H, int gx, const float* __restrict__ bg, const
         const uint32_t buf = (uint32_t)(c & 1);
         // chunk c+1 -> the other buffer (chunk c-1 has been walked and its parked splats moved out), chunk c+2 -> regs
         int cnt_next = 0;
-        if (c + 1 < nc) cnt_next = stage_chunk((int)(buf ^ 1u), mA, idA);
+        if (c + 1 < nc) cnt_next = stage_chunk(c + 1, (int)(buf ^ 1u), mA, idA);
         cp_async_commit_w();
         load_chunk(c + 2, mA, idA);
         cp_async_wait1_w();   // chunk c has landed (this thread's copies) ...

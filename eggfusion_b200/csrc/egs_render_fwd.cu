@@ -9,8 +9,10 @@
 //     can reach (one mask word); a warp then visits only its own hits (ballot + find-first-set).  The kernel is
 //     issue-bound (ncu: 89 % issue-active, DRAM 2 %), so instructions per (tile, surfel) are what matters;
 //   * splats are staged as packed 64-byte records (one gather per instance instead of eight);
-//   * for every (instance, warp block) the 32-bit mask of pixels that actually blended it is saved (32 B per
-//     instance): the backward walks exactly those pairs and never repeats the alpha / transmittance tests.
+//   * every warp appends {surfel id, 32-bit mask of the pixels that actually blended it} to the hit list of its
+//     8x4 block (HITLIST, 8 B per hit, depth order): the backward walks exactly those pairs, never repeats the
+//     alpha / transmittance tests and never scans list entries that missed its block.  The tile-wide backward
+//     variants get the same information as 8 mask words per instance (lane_masks) instead.
 // Per pixel the arithmetic order of the reference is kept: power, alpha = min(0.99, o*exp(power)), skip < 1/255,
 // stop (without blending) when T(1-alpha) < 1e-4, w = alpha*T, fma accumulation, T clamp at 1-1e-6.
 #include "egs_common.cuh"
@@ -36,13 +38,14 @@ __device__ __forceinline__ uint32_t block_mask_f(float x, float y, uint32_t ext,
     return m;
 }
 
+template <bool HITLIST>
 __global__ void __launch_bounds__(EGS_TILE_THREADS, 6)
 k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
                  BinView bn, long long cap, float* __restrict__ out_color, float* __restrict__ out_normal,
                  float* __restrict__ out_depth, float* __restrict__ out_opac) {
     __shared__ float4 s_rec[FWD_BATCH * 4];
     __shared__ uint32_t s_wm[FWD_BATCH];
-    __shared__ __align__(16) uint32_t s_lm[FWD_BATCH * 8];
+    __shared__ __align__(16) uint32_t s_lm[FWD_BATCH * 8];   // blend masks of the batch: [instance][block], HITLIST: [block][instance]
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
@@ -67,6 +70,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
             im.final_D[pix] = 0.f;
             im.n_contrib[pix] = 0u;
         }
+        if (HITLIST && threadIdx.x < 8) im.hit_count[8 * tile + threadIdx.x] = 0u;
         return;
     }
     const uint32_t* __restrict__ plist = bn.point_list + start;
@@ -75,12 +79,17 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
 
     const uint32_t rec_base = smem_addr(s_rec);
     const uint32_t wm_lane = smem_addr(s_wm) + 4u * (uint32_t)lane;    // this lane's slot of a 32-entry chunk
-    const uint32_t lm_warp = smem_addr(s_lm) + 4u * (uint32_t)warp;    // this warp's word of an entry's mask row
+    const uint32_t lm_warp = smem_addr(s_lm) + (HITLIST ? 4u * FWD_BATCH : 4u) * (uint32_t)warp;   // this warp's words
+    constexpr uint32_t LM_STRIDE = HITLIST ? 4u : 32u;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f;
     uint32_t last = 0;
     bool done = !inside;
+    // this block's hit list: entries 8*start + warp*n ... (at most n of them)
+    uint2* __restrict__ hseg = bn.hits + 8 * (size_t)start + (size_t)warp * (size_t)n;
+    uint32_t hcnt = 0u;
 
     for (int base = 0; base < n; base += FWD_BATCH) {
+        // also the barrier that keeps the previous batch's records alive until every warp is done with them
         if (__syncthreads_count(done) == EGS_TILE_THREADS) break;
         const int m = min(FWD_BATCH, n - base);
         uint32_t wm = 0u;
@@ -88,13 +97,15 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
             const uint32_t id = __ldg(plist + base + threadIdx.x);
             const float4* src = reinterpret_cast<const float4*>(rec + id);
             const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
-            s_rec[threadIdx.x * 4] = a; s_rec[threadIdx.x * 4 + 1] = b;
-            s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
             wm = block_mask_f(a.x, a.y, __float_as_uint(a.z), tile_x0, tile_y0);
+            // the extent word has served its purpose: the staged copy carries the surfel id in its place
+            s_rec[threadIdx.x * 4] = HITLIST ? make_float4(a.x, a.y, __uint_as_float(id), a.w) : a;
+            s_rec[threadIdx.x * 4 + 1] = b;
+            s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
         }
         s_wm[threadIdx.x] = wm;
-        reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
-        reinterpret_cast<uint4*>(s_lm)[2 * threadIdx.x + 1] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(s_lm)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(s_lm)[threadIdx.x + FWD_BATCH] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         if (!__all_sync(0xffffffffu, done)) {
             const int chunks = (m + 31) >> 5;
@@ -114,7 +125,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                     if (ok && test_T < 0.0001f) { done = true; ok = false; }   // stops WITHOUT blending this one
                     const unsigned bm = __ballot_sync(0xffffffffu, ok);
                     if (bm == 0u) continue;
-                    sts32(lm_warp + 32u * (uint32_t)j, bm);   // every lane stores the same word: one wavefront
+                    sts32(lm_warp + LM_STRIDE * (uint32_t)j, bm);   // every lane stores the same word: one wavefront
                     if (ok) {
                         const float w = __fmul_rn(alpha, T);
                         const float4 q2 = lds128(ra + 32u), q3 = lds128(ra + 48u);
@@ -128,15 +139,31 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                 }
                 if (__all_sync(0xffffffffu, done)) break;
             }
+            if (HITLIST) {
+                // append this batch's blended entries to the block's hit list, in list order: only this warp wrote
+                // (and reads) its row of s_lm, so no CTA barrier is needed
+                __syncwarp();
+                for (int c = 0; c < chunks; c++) {
+                    const uint32_t j = (uint32_t)(c * 32 + lane);
+                    const uint32_t mk = lds32(lm_warp + 4u * j);
+                    const unsigned hb = __ballot_sync(0xffffffffu, mk != 0u);
+                    if (mk != 0u)
+                        hseg[hcnt + (uint32_t)__popc(hb & ((1u << lane) - 1u))] = make_uint2(lds32(rec_base + 64u * j + 8u), mk);
+                    hcnt += (uint32_t)__popc(hb);
+                }
+            }
         }
-        __syncthreads();
-        // publish the blend masks of this batch: 32 contiguous bytes per instance
-        if ((int)threadIdx.x < m) {
-            uint4* dst = reinterpret_cast<uint4*>(bn.lane_masks + 8 * (size_t)(start + base + threadIdx.x));
-            dst[0] = reinterpret_cast<const uint4*>(s_lm)[2 * threadIdx.x];
-            dst[1] = reinterpret_cast<const uint4*>(s_lm)[2 * threadIdx.x + 1];
+        if (!HITLIST) {
+            __syncthreads();
+            // publish the blend masks of this batch: 32 contiguous bytes per instance
+            if ((int)threadIdx.x < m) {
+                uint4* dst = reinterpret_cast<uint4*>(bn.lane_masks + 8 * (size_t)(start + base + threadIdx.x));
+                dst[0] = reinterpret_cast<const uint4*>(s_lm)[2 * threadIdx.x];
+                dst[1] = reinterpret_cast<const uint4*>(s_lm)[2 * threadIdx.x + 1];
+            }
         }
     }
+    if (HITLIST && lane == 0) im.hit_count[8 * tile + warp] = hcnt;
     if (inside) {
         T = fminf(0.999999f, T);
         im.final_T[pix] = T;
@@ -155,7 +182,11 @@ cudaError_t launch_render_forward(const egs_frame& f, GeomView g, ImgView im, Bi
                                   float* out_color, float* out_normal, float* out_depth, float* out_opac,
                                   cudaStream_t s) {
     const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
-    k_render_forward<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, out_color,
-                                                          out_normal, out_depth, out_opac);
+    if (egs_bwd_variant() == 3)
+        k_render_forward<true><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
+                                                                    out_color, out_normal, out_depth, out_opac);
+    else
+        k_render_forward<false><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
+                                                                     out_color, out_normal, out_depth, out_opac);
     return cudaGetLastError();
 }
