@@ -58,6 +58,23 @@ SIGNATURES.update({
     "egt_solve_block": (C.c_int, [_P, _P, C.c_float, _P, _I32, _P]),
 })
 
+# include/eggmap.h
+class AdamHyper(C.Structure):
+    """struct egm_adam"""
+    _fields_ = [("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("lr_xyz", C.c_float), ("lr_f_dc", C.c_float), ("lr_f_rest", C.c_float), ("lr_opacity", C.c_float),
+                ("lr_scaling", C.c_float), ("lr_rotation", C.c_float), ("step", C.c_int32), ("reg_weight", C.c_float),
+                ("reg_weight_n", C.c_float)]
+
+
+EGM_TERMS, EGM_REG = 8, 4
+SIGNATURES.update({
+    "egm_loss_seed": (C.c_int, [_I32, _I32] + [_P] * 8 + [C.c_float] * 3 + [_P] * 5),
+    "egm_adam_step": (C.c_int, [_I32, _I32, C.POINTER(AdamHyper)] + [_P] * 27),
+    "egm_activate": (C.c_int, [_I32] + [_P] * 8),
+    "egm_loss_total": (C.c_int, [_P, _P, _I32, _I32] + [C.c_float] * 5 + [_I32, _I32, _P, _P]),
+})
+
 _lib = None
 
 

@@ -2,6 +2,8 @@
 // (eggfusion_b200/csrc/egs_surfel_math.cuh) for the CPU so that tests without a GPU can compare the exact
 // arithmetic the kernels run against the oracle.  Never loaded by the product path.
 #include "../../eggfusion_b200/csrc/egs_surfel_math.cuh"
+#include "../../eggfusion_b200/csrc/egm_math.cuh"
+#include <cmath>
 #include <cstring>
 
 static FrameConst make_fc(int W, int H, int D, int M, float tanfovx, float tanfovy, float cx, float cy, float mod,
@@ -69,6 +71,55 @@ void emu_surfel_backward(int P, int W, int H, int D, int M, float tanfovx, float
         memcpy(d_scales + 3 * (size_t)i, o.d_scale, 12);
         memcpy(d_rots + 4 * (size_t)i, o.d_rot, 16);
         memcpy(d_cov3D + 6 * (size_t)i, o.d_cov3D, 24);
+    }
+}
+
+// ---- mapping glue (egm_math.cuh): the same per-pixel / per-surfel sequence egm_mapping.cu runs -------------------
+void emu_cosdist(int n, const float* x1, const float* x2, float up, float* val, float* grad) {
+    for (int i = 0; i < n; i++) {
+        float d[3] = {0.f, 0.f, 0.f};
+        val[i] = egm_cosdist(x1 + 3 * i, x2 + 3 * i, up, d);
+        memcpy(grad + 3 * i, d, 12);
+    }
+}
+
+void emu_adam_geom(int P, int step, const float* lrs /* xyz, opacity, scaling, rotation */, float reg_w, float reg_wn,
+                   double nrm2, float* xyz, float* opacity_raw, float* scaling_raw, float* rotation_raw,
+                   const float* d_xyz, const float* d_opacity, const float* d_scales, const float* d_rot, float* m_xyz,
+                   float* v_xyz, float* m_op, float* v_op, float* m_sc, float* v_sc, float* m_rot, float* v_rot,
+                   const float* pos0, const float* normal0, float* g_xyz, float* g_op, float* g_sc, float* g_rot,
+                   float* act_o, float* act_s, float* act_r) {
+    const double beta1 = 0.9, beta2 = 0.999;
+    const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+    EgmAdamConst c;
+    c.beta1 = (float)beta1; c.beta2 = (float)beta2;
+    c.one_m_beta1 = (float)(1.0 - beta1); c.one_m_beta2 = (float)(1.0 - beta2);
+    c.eps = 1e-8f; c.bc2_sqrt = (float)std::sqrt(bc2);
+    float nss[4];
+    for (int k = 0; k < 4; k++) nss[k] = (float)(-((double)lrs[k] / bc1));
+    const float pos_scale = nrm2 > 0.0 ? reg_w / (float)std::sqrt(nrm2) : 0.f;
+    for (int i = 0; i < P; i++) {
+        EgmSurfel p, g;
+        for (int k = 0; k < 3; k++) {
+            p.x[k] = xyz[3 * i + k]; p.s[k] = scaling_raw[3 * i + k];
+            g.x[k] = d_xyz[3 * i + k]; g.s[k] = d_scales[3 * i + k];
+        }
+        for (int k = 0; k < 4; k++) { p.q[k] = rotation_raw[4 * i + k]; g.q[k] = d_rot[4 * i + k]; }
+        p.o = opacity_raw[i]; g.o = d_opacity[i];
+        egm_surfel_raw_grads(p, g, reg_w > 0.f, pos_scale, reg_w * reg_wn / (float)P, pos0 + 3 * i, normal0 + 3 * i);
+        memcpy(g_xyz + 3 * i, g.x, 12); memcpy(g_sc + 3 * i, g.s, 12); memcpy(g_rot + 4 * i, g.q, 16); g_op[i] = g.o;
+        for (int k = 0; k < 3; k++) {
+            xyz[3 * i + k] = egm_adam_update(p.x[k], g.x[k], m_xyz[3 * i + k], v_xyz[3 * i + k], c, nss[0]);
+            scaling_raw[3 * i + k] = egm_adam_update(p.s[k], g.s[k], m_sc[3 * i + k], v_sc[3 * i + k], c, nss[2]);
+        }
+        opacity_raw[i] = egm_adam_update(p.o, g.o, m_op[i], v_op[i], c, nss[1]);
+        for (int k = 0; k < 4; k++)
+            rotation_raw[4 * i + k] = egm_adam_update(p.q[k], g.q[k], m_rot[4 * i + k], v_rot[4 * i + k], c, nss[3]);
+        act_o[i] = egm_sigmoid(opacity_raw[i]);
+        for (int k = 0; k < 3; k++) act_s[3 * i + k] = expf(scaling_raw[3 * i + k]);
+        EgmRot rot;
+        egm_normalize_quat(rotation_raw + 4 * i, rot);
+        for (int k = 0; k < 4; k++) act_r[4 * i + k] = egm_nan_to_num(rot.qh[k]);
     }
 }
 }

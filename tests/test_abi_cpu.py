@@ -10,19 +10,20 @@ import torch
 
 from util import ROOT
 
-HEADERS = [os.path.join(ROOT, "include", "eggsplat.h"), os.path.join(ROOT, "include", "eggtrack.h")]
+HEADERS = [os.path.join(ROOT, "include", "eggsplat.h"), os.path.join(ROOT, "include", "eggtrack.h"),
+           os.path.join(ROOT, "include", "eggmap.h")]
 
 
 def declared_symbols():
     src = "".join(open(h).read() for h in HEADERS)
-    return sorted(set(re.findall(r"EGS_API\s+[\w\s\*]+?\b(eg[st]_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"EGS_API\s+[\w\s\*]+?\b(eg[stm]_\w+)\s*\(", src)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():
     import eggfusion_b200
     so = eggfusion_b200.build()
     out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
-    exported = sorted(set(re.findall(r"\bT\s+(eg[st]_\w+)", out)))
+    exported = sorted(set(re.findall(r"\bT\s+(eg[stm]_\w+)", out)))
     decl = declared_symbols()
     assert len(decl) >= 17
     assert exported == decl

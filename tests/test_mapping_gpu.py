@@ -1,0 +1,185 @@
+"""GPU parity of the mapping-iteration glue (include/eggmap.h) through the C ABI: against the numpy
+oracle, against the goldens produced by the reference's own python code, and the two host-side levels
+(autograd drop-in vs FusedMapper) against each other."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import GOLDEN_DIR, rel_err, syn
+from oracle import mapping_oracle as mo
+from test_mapping_cpu import NAMES, knife_edge_rows, mg
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def n(x):
+    return x.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(mg.CASES))
+def test_loss_and_seeds_match_oracle_and_reference_golden(name):
+    from eggfusion_b200 import mapping as M
+    raw, its, (cw, dw, nw, rw, rwn), lr = mg.case_inputs(name)
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    w = M.MappingWeights(cw, dw, nw, 0.0, rwn)
+    for k, it in enumerate(its):
+        terms, gc, gd, gn = M.loss_seed(t(it["est_color"]), t(it["est_depth"]), t(it["est_normal"]), t(it["ref_color"]),
+                                        t(it["ref_depth"]), t(it["ref_normal"]), t(it["rgb_mask"]), t(it["geo_mask"]), w)
+        out = n(M.loss_total(terms, w))
+        o = mo.loss_seed(it["est_color"], it["est_depth"], it["est_normal"], it["ref_color"], it["ref_depth"],
+                         it["ref_normal"], it["rgb_mask"], it["geo_mask"], cw, dw, nw)
+        assert int(n(terms)[0]) == o["count"] and n(terms)[4] == 0
+        for got, key in ((out[1], "color_loss"), (out[2], "depth_loss"), (out[3], "normal_loss"), (out[0], "image_loss")):
+            assert abs(got - o[key]) <= 1e-5 * abs(o[key]), key
+        for got, okey, gkey in ((gc, "dL_dcolor", "seed_color"), (gd, "dL_ddepth", "seed_depth"), (gn, "dL_dnormal", "seed_normal")):
+            assert rel_err(n(got), o[okey]) <= 1e-5, okey
+            assert rel_err(n(got), gold[f"{gkey}_{k}"]) <= TOL, gkey
+        if rw == 0:
+            assert abs(out[0] - gold[f"loss_{k}"]) <= 1e-5 * abs(gold[f"loss_{k}"])
+
+
+def test_loss_edge_cases():
+    from eggfusion_b200 import mapping as M
+    raw, its, (cw, dw, nw, rw, rwn), lr = mg.case_inputs("mapping_deg0_noreg")
+    it = its[0]
+    w = M.MappingWeights(cw, dw, nw)
+    z = torch.zeros_like(t(it["rgb_mask"]))
+    terms, gc, gd, gn = M.loss_seed(t(it["est_color"]), t(it["est_depth"]), t(it["est_normal"]), t(it["ref_color"]),
+                                    t(it["ref_depth"]), t(it["ref_normal"]), z, t(it["geo_mask"]), w)
+    out = n(M.loss_total(terms, w))
+    assert np.isnan(out[1]) and out[2] == 0 and out[3] == 0 and np.isnan(out[0])      # mean of an empty tensor
+    assert not gc.any() and not gd.any() and not gn.any()
+    # absent depth / normal maps and no geo mask; NaN inputs are counted (check_nan of the reference)
+    ec = it["est_color"].copy()
+    ec[0, 0, 0] = np.nan
+    terms, gc, gd, gn = M.loss_seed(t(ec), t(it["est_depth"]), t(it["est_normal"]), t(it["ref_color"]), None, None,
+                                    t(it["rgb_mask"]), None, w)
+    out = n(M.loss_total(terms, w, False, False))
+    assert n(terms)[4] == 1 and out[2] == 0 and out[3] == 0 and not gd.any() and not gn.any()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.loss_seed(torch.zeros(3, 4, 4), torch.zeros(1, 4, 4), torch.zeros(3, 4, 4), torch.zeros(4, 4, 3), None, None,
+                    torch.ones(4, 4, dtype=torch.bool), None, w)
+
+
+def _forced_optimizer(M, name, gold, k, raw0, weights, lr):
+    """FrameBatchOptimizer holding the reference's parameters / Adam state after iteration k-1 (each step on its own)."""
+    opt = M.FrameBatchOptimizer({nm: t(raw0[nm]) for nm in NAMES}, M.LrParams(**lr), weights)
+    if k > 0:
+        prm = {nm: gold[f"param_{nm}_{k - 1}"] for nm in NAMES}
+        opt.xyz.copy_(t(prm["xyz"])); opt.scaling_raw.copy_(t(prm["scaling"]))
+        opt.rotation_raw.copy_(t(prm["rotation"])); opt.opacity_raw.copy_(t(prm["opacity"]))
+        opt.shs.copy_(t(np.concatenate([prm["features_dc"], prm["features_rest"]], axis=1)))
+        cat = lambda s: np.concatenate([gold[f"{s}_features_dc_{k - 1}"], gold[f"{s}_features_rest_{k - 1}"]], axis=1)
+        for key, nm in (("xyz", "xyz"), ("opacity", "opacity"), ("scaling", "scaling"), ("rotation", "rotation")):
+            opt.state[key][0].copy_(t(gold[f"m_{nm}_{k - 1}"])); opt.state[key][1].copy_(t(gold[f"v_{nm}_{k - 1}"]))
+        opt.state["shs"][0].copy_(t(cat("m"))); opt.state["shs"][1].copy_(t(cat("v")))
+        opt.step_count = k
+        nrm2 = float(((raw0["xyz"].astype(np.float64) - prm["xyz"]) ** 2).sum())
+        opt.reg[(k + 1) & 1] = nrm2
+    return opt
+
+
+@pytest.mark.parametrize("name", list(mg.CASES))
+def test_adam_step_matches_reference_golden(name):
+    from eggfusion_b200 import mapping as M
+    raw0, its, (cw, dw, nw, rw, rwn), lr = mg.case_inputs(name)
+    gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    w = M.MappingWeights(cw, dw, nw, rw, rwn)
+    edge = knife_edge_rows(name, gold)
+    for k, it in enumerate(its):
+        opt = _forced_optimizer(M, name, gold, k, raw0, w, lr)
+        if k == 0:
+            assert rel_err(n(opt.normal0), gold["normal0"]) <= 1e-6
+        start = {nm: n(v).copy() for nm, v in opt.raw_params().items()}
+        opt.step({"xyz": t(it["G_xyz"]), "shs": t(it["G_shs"]), "opacity": t(it["G_opacity"]), "scales": t(it["G_scales"]),
+                  "rotations": t(it["G_rot"])})
+        got = {nm: n(v) for nm, v in opt.raw_params().items()}
+        st = {"xyz": opt.state["xyz"], "opacity": opt.state["opacity"], "scaling": opt.state["scaling"],
+              "rotation": opt.state["rotation"], "features_dc": tuple(s[:, :1] for s in opt.state["shs"]),
+              "features_rest": tuple(s[:, 1:] for s in opt.state["shs"])}
+        for nm in NAMES:
+            keep = ~edge[k] if nm == "rotation" else slice(None)
+            dg, do = (gold[f"param_{nm}_{k}"] - start[nm])[keep], (got[nm] - start[nm])[keep]
+            if dg.size and np.abs(dg).max() > 0:
+                assert rel_err(do, dg) <= 1e-3, (nm, k, rel_err(do, dg))
+            assert rel_err(got[nm][keep], gold[f"param_{nm}_{k}"][keep]) <= 1e-6, (nm, k)
+            if dg.size:
+                assert rel_err(n(st[nm][0])[keep], gold[f"m_{nm}_{k}"][keep]) <= TOL, (nm, k, "m")
+                assert rel_err(n(st[nm][1])[keep], gold[f"v_{nm}_{k}"][keep]) <= TOL, (nm, k, "v")
+        for key, act in (("opacity", opt.opacity), ("scales", opt.scales), ("rotations", opt.rotations)):
+            keep = ~edge[k] if key == "rotations" else slice(None)
+            assert rel_err(n(act)[keep], gold[f"act_{key}_{k}"][keep]) <= 1e-6, key
+        if rw > 0:   # total loss of the iteration = image terms + reg_weight * regulariser (available after the step)
+            terms, *_ = M.loss_seed(t(it["est_color"]), t(it["est_depth"]), t(it["est_normal"]), t(it["ref_color"]),
+                                    t(it["ref_depth"]), t(it["ref_normal"]), t(it["rgb_mask"]), t(it["geo_mask"]), w)
+            total = n(opt.loss_values(terms))[0]
+            assert abs(total - gold[f"loss_{k}"]) <= 1e-5 * abs(gold[f"loss_{k}"]), (total, gold[f"loss_{k}"])
+
+
+def test_autograd_level_equals_fused_mapper():
+    """The same two iterations through (GaussianRasterizer + compute_loss + loss.backward() + opt.step()) and through
+    FusedMapper.iterate (no autograd, persistent buffers) give the same parameters and losses."""
+    import eggfusion_b200 as E
+    from eggfusion_b200 import mapping as M
+    W, H, P, deg = 160, 96, 3000, 3
+    cam = syn.default_camera(W, H, syn.look_from((0.05, -0.03, 0.02), 0.05, -0.04))
+    sc = syn.make_scene(P, syn.default_camera(W, H), layers=2, sh_degree=deg)
+    r = np.random.default_rng(5)
+    raw = {"xyz": sc["xyz"], "features_dc": sc["shs"][:, :1].copy(), "features_rest": sc["shs"][:, 1:].copy(),
+           "scaling": np.log(np.maximum(sc["scales"], 1e-30)).astype(np.float32), "rotation": sc["rotations"] * 1.7,
+           "opacity": np.log(sc["opacity"] / (1 - sc["opacity"])).astype(np.float32)}
+    raw["scaling"][:, 2] = -1.0e10
+    frame = {"color_map": t(r.uniform(0, 1, (H, W, 3)).astype(np.float32)),
+             "depth_map": t(r.uniform(1, 3, (H, W, 1)).astype(np.float32)),
+             "normal_map_c": t(np.tile(np.array([0, 0, -1], np.float32), (H, W, 1)))}
+    masks = (t(r.uniform(0, 1, (H, W)) < 0.9), t(r.uniform(0, 1, (H, W)) < 0.9))
+    w = M.MappingWeights(1.0, 1.0, 1.0, 10.0, 1.0)
+    lr = M.LrParams(1e-4, 1e-3, 1e-3, 5e-4, 1e-3)
+    settings = E.GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=t(np.zeros(3, np.float32)),
+        scale_modifier=1.0, viewmatrix=t(cam.viewmatrix), projmatrix=t(cam.projmatrix), sh_degree=deg,
+        campos=t(cam.campos), prefiltered=False, debug=False, cx=cam.cx, cy=cam.cy)
+
+    opt_a = M.FrameBatchOptimizer({k: t(v) for k, v in raw.items()}, lr, w)
+    losses_a = []
+    for _ in range(2):
+        tp = opt_a.total_params
+        color, normal, depth, opac, _a, _r = E.GaussianRasterizer(settings)(
+            means3D=tp["xyz"], opacities=tp["opacity"], shs=tp["shs"], scales=tp["scales"], rotations=tp["rotations"])
+        loss = M.compute_loss({"color": color, "depth": depth, "normal": normal}, frame, masks, w)
+        loss.backward()
+        losses_a.append(float(loss))
+        opt_a.step()
+
+    opt_b = M.FrameBatchOptimizer({k: t(v) for k, v in raw.items()}, lr, w)
+    fm = M.FusedMapper(opt_b, W, H, capacity=200000, sh_degree=deg)
+    losses_b = [n(fm.iterate(settings, frame, masks)).copy() for _ in range(2)]
+    assert fm.ctx.read_counters()[2] == 0
+    for i in range(2):
+        image_b = losses_b[i][0] - w.reg_weight * losses_b[i][4]
+        assert abs(image_b - losses_a[i]) <= 1e-5 * abs(losses_a[i])
+    ra, rb = opt_a.raw_params(), opt_b.raw_params()
+    for k in ra:
+        step = n(ra[k]) - raw[k]
+        if np.abs(step).max() > 0:
+            assert rel_err(n(rb[k]) - raw[k], step) <= 2e-3, k
+        assert rel_err(n(rb[k]), n(ra[k])) <= 1e-6, k
+    # write_back mirrors the parameters into a GaussianSurfels-like object
+    class S:
+        pass
+    s = S()
+    for k, v in raw.items():
+        setattr(s, "_" + k, t(v).clone())
+    o = M.FrameBatchOptimizer(s, lr, w)
+    o.step({"xyz": torch.ones_like(o.xyz), "shs": torch.ones_like(o.shs), "opacity": torch.ones_like(o.opacity),
+            "scales": torch.ones_like(o.scales), "rotations": torch.ones_like(o.rotations)})
+    o.write_back()
+    assert not torch.equal(s._features_dc, t(raw["features_dc"])) and torch.equal(s._features_dc, o.shs[:, :1])
