@@ -163,6 +163,141 @@ def dist_env():
     return rank, world, local
 
 
+# ------------------------------------------------------------------------------------------------ mapping iteration
+MAP_WEIGHTS = dict(color_weight=1.0, depth_weight=1.0, normal_weight=1.0, reg_weight=10.0, reg_weight_n=1.0)
+MAP_LR = dict(position_lr=1e-5, feature_lr=1e-3, opacity_lr=1e-5, scaling_lr=5e-4, rotation_lr=1e-4)  # configs/replica/base.yaml:53-57,72-76
+
+
+def mapping_inputs(scene, cams, dev):
+    """Raw (pre-activation) GaussianSurfels parameters of the scene + one keyframe map per camera (device tensors)."""
+    import torch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sc = np.log(np.maximum(scene["scales"], 1e-30)).astype(np.float32)
+    sc[:, 2] = -1.0e10                                   # gaussian_surfels.py:185-186
+    op = np.clip(scene["opacity"], 1e-4, 1 - 1e-4)
+    raw = {"xyz": t(scene["xyz"]), "features_dc": t(scene["shs"][:, :1]), "features_rest": t(scene["shs"][:, 1:]),
+           "scaling": t(sc), "rotation": t(scene["rotations"]), "opacity": t(np.log(op / (1 - op)).astype(np.float32))}
+    H, W = cams[0].height, cams[0].width
+    frames = []
+    for i in range(len(cams)):
+        r = np.random.default_rng(700 + i)
+        nrm = r.standard_normal((H, W, 3)).astype(np.float32) * 0.1 + np.array([0, 0, -1], np.float32)
+        nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+        frames.append(({"color_map": t(r.uniform(0, 1, (H, W, 3)).astype(np.float32)),
+                        "depth_map": t(r.uniform(1, 3, (H, W, 1)).astype(np.float32)), "normal_map_c": t(nrm)},
+                       (t(r.uniform(0, 1, (H, W)) < 0.95), t(r.uniform(0, 1, (H, W)) < 0.95))))
+    return raw, frames
+
+
+def time_loop(fn, warmup, steps, sync_each=False):
+    import torch
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(warmup, warmup + steps):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def reference_mapping_iteration_factory(rast_mod, raw, frames, settings, deg):
+    """One iteration of Mapper.frame_batch_optimization (/root/reference/src/core/mapper.py:336-368) as the reference
+    runs it: torch activations (Mapper.total_params :565-585 over GaussianSurfels.get_* gaussian_surfels.py:345-425),
+    the reference rasterizer through Renderer.render's call (render.py:53-104), Mapper.compute_loss (:381-444, incl.
+    its ten check_nan passes :21-27 and the NaN guard), loss.backward(), torch.optim.Adam over the six parameter
+    groups (gaussian_surfels.py:134-150), zero_grad, loss.item() (progress bar).  Plain torch ops; /root/reference is
+    not present on the GPU box, so the expressions are restated here."""
+    import torch
+    import torch.nn.functional as F
+    prm = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+    lr = MAP_LR
+    opt = torch.optim.Adam([
+        {"params": [prm["xyz"]], "lr": lr["position_lr"]}, {"params": [prm["features_dc"]], "lr": lr["feature_lr"]},
+        {"params": [prm["features_rest"]], "lr": lr["feature_lr"] / 20.0},
+        {"params": [prm["opacity"]], "lr": lr["opacity_lr"]}, {"params": [prm["scaling"]], "lr": lr["scaling_lr"]},
+        {"params": [prm["rotation"]], "lr": lr["rotation_lr"]}], lr=0.0)
+
+    def build_rotation(r):
+        norm = torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3])
+        q = r / norm[:, None]
+        R = torch.zeros((q.size(0), 3, 3), device=r.device)
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w * z); R[:, 0, 2] = 2 * (x * z + w * y)
+        R[:, 1, 0] = 2 * (x * y + w * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w * x)
+        R[:, 2, 0] = 2 * (x * z - w * y); R[:, 2, 1] = 2 * (y * z + w * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+        return R
+
+    def get_normal():
+        scales = torch.exp(prm["scaling"])
+        R = build_rotation(F.normalize(prm["rotation"]))
+        idx = torch.argmin(scales, dim=1)
+        nrm = torch.gather(R.transpose(1, 2), 1, idx.unsqueeze(1).unsqueeze(2).expand(-1, -1, 3))[:, 0, :]
+        return nrm / (torch.norm(nrm, dim=-1, keepdim=True) + 1e-8)
+
+    def total_params():
+        scaling = torch.exp(prm["scaling"])
+        mn, _ = torch.min(scaling, dim=1)
+        return {"xyz": prm["xyz"].contiguous(), "opacity": torch.sigmoid(prm["opacity"]).contiguous(),
+                "scales": scaling.contiguous(),
+                "rotations": torch.nan_to_num(F.normalize(prm["rotation"]), nan=1.0).contiguous(),
+                "normal": get_normal().contiguous(),
+                "shs": torch.cat((prm["features_dc"], prm["features_rest"]), dim=1).contiguous(),
+                "radius": ((torch.sum(scaling, dim=1) - mn) / 2).contiguous()}
+
+    def check_nan(x):
+        bad = 0
+        if torch.isnan(x).any():
+            bad += 1
+        if torch.isinf(x).any():
+            bad += 1
+        if (x.abs() > 1e6).any():
+            bad += 1
+        return bad
+
+    geo = {"position": prm["xyz"].detach().clone(), "normal": get_normal().detach()}
+    w = MAP_WEIGHTS
+    H, W = settings[0].image_height, settings[0].image_width
+    losses = []
+
+    def iteration(i):
+        ci = i % len(frames)
+        fmap, (rgb_mask, geo_mask) = frames[ci]
+        tp = total_params()
+        tile_mask = torch.ones((H + 15) // 16, (W + 15) // 16, dtype=torch.int32).cuda()
+        out = rast_mod.GaussianRasterizer(raster_settings=settings[ci])(
+            means3D=tp["xyz"], opacities=tp["opacity"], shs=tp["shs"], colors_precomp=None, scales=tp["scales"],
+            rotations=tp["rotations"], cov3D_precomp=None, tile_mask=tile_mask)
+        est_color, est_normal, est_depth = out[0].permute([1, 2, 0]), out[1].permute([1, 2, 0]), out[2].permute([1, 2, 0])
+        mask = rgb_mask & geo_mask
+        for x in (out[0], out[2], out[1], fmap["color_map"], fmap["depth_map"], fmap["normal_map_c"], geo["position"],
+                  geo["normal"], prm["xyz"], get_normal()):
+            check_nan(x)
+        color_loss = torch.abs(fmap["color_map"] - est_color)[mask].mean()
+        depth_loss = torch.tensor(0.0, device=est_color.device)
+        normal_loss = torch.tensor(0.0, device=est_color.device)
+        depth_error = fmap["depth_map"] - est_depth
+        if mask.any():
+            depth_loss = torch.abs(depth_error[mask]).mean()
+        cos_dist = 1 - F.cosine_similarity(fmap["normal_map_c"], est_normal, dim=-1).clamp(-1 + 1e-6, 1 - 1e-6)
+        if mask.any():
+            normal_loss = torch.abs(cos_dist[mask]).mean()
+        reg_position = torch.norm(geo["position"] - prm["xyz"])
+        reg_normal = 1 - F.cosine_similarity(geo["normal"], get_normal(), dim=-1).clamp(-1 + 1e-6, 1 - 1e-6)
+        reg_loss = reg_position.mean() + w["reg_weight_n"] * reg_normal.abs().mean()
+        total = (w["color_weight"] * color_loss + w["depth_weight"] * depth_loss + w["normal_weight"] * normal_loss
+                 + w["reg_weight"] * reg_loss)
+        if torch.isnan(total):
+            raise RuntimeError("NaN in loss")
+        total.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(total.item())
+    return iteration, losses
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_baseline_sample(scene, cams, grads, deg, budget_s=12.0):
     """Oracle port (C, OpenMP, all host cores) on a bounded sample of the same workload: whole frames (forward +
@@ -350,6 +485,33 @@ def run_ours(args):
                "frames_per_s": 1e3 / ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 16,
                "api": "eggfusion_b200.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"}
 
+    mapping = None
+    if world == 1 and not args.no_mapping:
+        from eggfusion_b200 import mapping as MP
+        R.config.capacity = "exact"
+        torch.cuda.empty_cache()
+        raw, frames = mapping_inputs(scene, cams, dev)
+        mopt = MP.FrameBatchOptimizer(raw, MP.LrParams(**MAP_LR), MP.MappingWeights(**MAP_WEIGHTS))
+        fm = MP.FusedMapper(mopt, W, H, cap, deg)
+        host_loss = torch.zeros((args.steps + max(3, args.warmup) + 8, 5), dtype=torch.float32).pin_memory()
+
+        def map_async(i):
+            host_loss[i % host_loss.shape[0]].copy_(fm.iterate(settings[i % len(settings)], *frames[i % len(frames)]),
+                                                    non_blocking=True)
+
+        def map_sync(i):
+            return float(fm.iterate(settings[i % len(settings)], *frames[i % len(frames)])[0].item())
+        ms_async = time_loop(map_async, max(3, args.warmup), args.steps)
+        ms_sync = time_loop(map_sync, max(3, args.warmup), args.steps)
+        assert fm.ctx.read_counters()[2] == 0, "binning capacity overflow in the mapping loop"
+        mapping = {"ms_per_iter": ms_async, "iters_per_s": 1e3 / ms_async, "ms_per_iter_loss_item_each_iter": ms_sync,
+                   "last_loss": float(host_loss[(max(3, args.warmup) + args.steps - 1) % host_loss.shape[0], 0]),
+                   "what": "one Mapper.frame_batch_optimization iteration (activations, render, compute_loss incl. "
+                           "regulariser, backward, Adam over all 6 groups) = eggfusion_b200.mapping.FusedMapper.iterate; "
+                           "ms_per_iter: loss copied to pinned host memory asynchronously, "
+                           "ms_per_iter_loss_item_each_iter: blocking loss.item() every iteration like the reference loop",
+                   "gpu_launches_per_iter": 7 + 2 + 1 + 2}
+        del fm, mopt
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -394,6 +556,7 @@ def run_ours(args):
         "clocks": clocks,
         "gpu_launches": 7 * args.steps * world,
         "e2e": e2e,
+        "mapping_iter": mapping,
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)
@@ -511,6 +674,15 @@ def run_reference(args):
     b.record()
     torch.cuda.synchronize()
     ms_e2e = a.elapsed_time(b) / args.steps
+    mapping = None
+    if not args.no_mapping:
+        raw, frames = mapping_inputs(scene, cams, dev)
+        it, mlosses = reference_mapping_iteration_factory(ref, raw, frames, settings, deg)
+        ms_map = time_loop(it, max(3, args.warmup), args.steps)
+        mapping = {"ms_per_iter": ms_map, "iters_per_s": 1e3 / ms_map, "last_loss": mlosses[-1],
+                   "what": "one Mapper.frame_batch_optimization iteration with the reference rasterizer and the "
+                           "reference's torch glue (activations, compute_loss incl. check_nan, backward, torch Adam, "
+                           "loss.item())"}
     line = {
         "impl": "reference", "device": "cuda (unmodified diff-gaussian-surfels compiled for sm_100a, oracle/_ref)",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -526,6 +698,7 @@ def run_reference(args):
                 "frames_per_s": 1e3 / ms_e2e, "h2d_bytes_per_step": 4 * (4 * H * W) + 4 * 35,
                 "d2h_bytes_per_step": 4 + 4 + 8 * 8160,
                 "api": "diff_gaussian_rasterization.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"},
+        "mapping_iter": mapping,
     }
     print(json.dumps(line))
 
@@ -539,6 +712,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mapping", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
