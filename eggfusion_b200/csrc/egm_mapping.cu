@@ -53,6 +53,42 @@ k_mask_count(long long n, const uint8_t* __restrict__ rgb_mask, const uint8_t* _
     block_accumulate<1>(c, terms + EGM_T_COUNT);
 }
 
+// one pixel of compute_loss: accumulates the partial sums and returns the seeds
+struct PixelIn { float ec[3], en[3], ed, rc[3], rn[3], rd; bool m; };
+struct PixelOut { float gc[3], gn[3], gd; };
+__device__ __forceinline__ void loss_pixel(const PixelIn& p, bool have_depth, bool have_normal, float up_c, float up_d,
+                                           float up_n, double (&acc)[4], PixelOut& o) {
+    int nans = (p.ed != p.ed) + (p.rd != p.rd);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        nans += (p.ec[c] != p.ec[c]) + (p.en[c] != p.en[c]) + (p.rc[c] != p.rc[c]) + (p.rn[c] != p.rn[c]);
+    acc[3] += (double)nans;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { o.gc[c] = 0.f; o.gn[c] = 0.f; }
+    o.gd = 0.f;
+    if (p.m) {
+        // color_loss = |ref - est|[mask].mean()                                        mapper.py:411
+        float sc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float x = p.rc[c] - p.ec[c];
+            sc += fabsf(x);
+            o.gc[c] = -egm_sign(x) * up_c;
+        }
+        acc[0] += (double)sc;
+        if (have_depth) {   // depth_loss = |ref - est|[mask].mean()                    mapper.py:414-418
+            const float x = p.rd - p.ed;
+            acc[1] += (double)fabsf(x);
+            o.gd = -egm_sign(x) * up_d;
+        }
+        if (have_normal)    // normal_loss = |1 - cos.clamp|[mask].mean()               mapper.py:421-425
+            acc[2] += (double)egm_cosdist(p.rn, p.en, up_n, o.gn);
+    }
+}
+
+// VEC = 4: a thread owns 4 consecutive pixels -> every access is a 16-byte vector (channel-major float4 per
+// channel, pixel-major 3 x float4 per map, masks as one 32-bit word); VEC = 1: generic tail / unaligned fallback.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_loss_seed(long long n, const float* __restrict__ est_color, const float* __restrict__ est_depth,
             const float* __restrict__ est_normal, const float* __restrict__ ref_color,
@@ -64,46 +100,67 @@ k_loss_seed(long long n, const float* __restrict__ est_color, const float* __res
     const float up_c = cnt > 0.0 ? (float)((double)cw / (3.0 * cnt)) : 0.f;
     const float up_d = cnt > 0.0 ? (float)((double)dw / cnt) : 0.f;
     const float up_n = cnt > 0.0 ? (float)((double)nw / cnt) : 0.f;
+    const bool have_depth = ref_depth != nullptr && dw > 0.f, have_normal = ref_normal != nullptr && nw > 0.f;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};   // colour, depth, normal, NaN count
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const bool m = rgb_mask[i] != 0 && (geo_mask == nullptr || geo_mask[i] != 0);
-        float ec[3], en[3], rc[3], rn[3] = {0.f, 0.f, 0.f};
+    const long long i0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * VEC;
+    if (i0 < n) {
+        PixelIn p[VEC];
+        PixelOut o[VEC];
+        if (VEC == 4) {
+            union F4 { float4 v; float f[4]; };
+            union F12 { float4 v[3]; float f[12]; };
+            F4 c[3], nn[3], d, rdv;
+            F12 rc, rn;
+            rdv.v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            ec[c] = est_color[c * n + i];
-            en[c] = est_normal[c * n + i];
-            rc[c] = ref_color[3 * i + c];
-            if (ref_normal) rn[c] = ref_normal[3 * i + c];
-        }
-        const float ed = est_depth[i];
-        const float rd = ref_depth ? ref_depth[i] : 0.f;
-        int nans = (ed != ed) + (rd != rd);
-#pragma unroll
-        for (int c = 0; c < 3; c++) nans += (ec[c] != ec[c]) + (en[c] != en[c]) + (rc[c] != rc[c]) + (rn[c] != rn[c]);
-        acc[3] += (double)nans;
-        float gc[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f}, gd = 0.f;
-        if (m) {
-            // color_loss = |ref - est|[mask].mean()                                        mapper.py:411
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float x = rc[c] - ec[c];
-                acc[0] += (double)fabsf(x);
-                gc[c] = -egm_sign(x) * up_c;
+            for (int k = 0; k < 3; k++) {
+                c[k].v = *reinterpret_cast<const float4*>(est_color + k * n + i0);
+                nn[k].v = *reinterpret_cast<const float4*>(est_normal + k * n + i0);
+                rc.v[k] = reinterpret_cast<const float4*>(ref_color + 3 * i0)[k];
+                rn.v[k] = ref_normal ? reinterpret_cast<const float4*>(ref_normal + 3 * i0)[k] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (ref_depth && dw > 0.f) {   // depth_loss = |ref - est|[mask].mean()         mapper.py:414-418
-                const float x = rd - ed;
-                acc[1] += (double)fabsf(x);
-                gd = -egm_sign(x) * up_d;
-            }
-            if (ref_normal && nw > 0.f)    // normal_loss = |1 - cos.clamp|[mask].mean()    mapper.py:421-425
-                acc[2] += (double)egm_cosdist(rn, en, up_n, gn);
-        }
+            d.v = *reinterpret_cast<const float4*>(est_depth + i0);
+            if (ref_depth) rdv.v = *reinterpret_cast<const float4*>(ref_depth + i0);
+            const uint32_t m0 = *reinterpret_cast<const uint32_t*>(rgb_mask + i0);
+            const uint32_t m1 = geo_mask ? *reinterpret_cast<const uint32_t*>(geo_mask + i0) : 0x01010101u;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            g_color[c * n + i] = gc[c];
-            g_normal[c * n + i] = gn[c];
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    p[j].ec[k] = c[k].f[j]; p[j].en[k] = nn[k].f[j];
+                    p[j].rc[k] = rc.f[3 * j + k]; p[j].rn[k] = rn.f[3 * j + k];
+                }
+                p[j].ed = d.f[j]; p[j].rd = rdv.f[j];
+                p[j].m = ((m0 >> (8 * j)) & 0xffu) != 0u && ((m1 >> (8 * j)) & 0xffu) != 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) loss_pixel(p[j], have_depth, have_normal, up_c, up_d, up_n, acc, o[j]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                *reinterpret_cast<float4*>(g_color + k * n + i0) = make_float4(o[0].gc[k], o[1].gc[k], o[2].gc[k], o[3].gc[k]);
+                *reinterpret_cast<float4*>(g_normal + k * n + i0) = make_float4(o[0].gn[k], o[1].gn[k], o[2].gn[k], o[3].gn[k]);
+            }
+            *reinterpret_cast<float4*>(g_depth + i0) = make_float4(o[0].gd, o[1].gd, o[2].gd, o[3].gd);
+        } else {
+            const long long i = i0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                p[0].ec[k] = est_color[k * n + i];
+                p[0].en[k] = est_normal[k * n + i];
+                p[0].rc[k] = ref_color[3 * i + k];
+                p[0].rn[k] = ref_normal ? ref_normal[3 * i + k] : 0.f;
+            }
+            p[0].ed = est_depth[i];
+            p[0].rd = ref_depth ? ref_depth[i] : 0.f;
+            p[0].m = rgb_mask[i] != 0 && (geo_mask == nullptr || geo_mask[i] != 0);
+            loss_pixel(p[0], have_depth, have_normal, up_c, up_d, up_n, acc, o[0]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                g_color[k * n + i] = o[0].gc[k];
+                g_normal[k * n + i] = o[0].gn[k];
+            }
+            g_depth[i] = o[0].gd;
         }
-        g_depth[i] = gd;
     }
     block_accumulate<4>(acc, terms + EGM_T_COLOR);
 }
@@ -155,17 +212,50 @@ struct GeomArgs {
     float *opacity, *scales, *rotations;
 };
 
-__global__ void __launch_bounds__(128)
+// [P,3] arrays are staged through shared memory: a CTA of 128 surfels moves 384 consecutive floats per array with
+// fully coalesced accesses and each thread then picks its 3 values at stride 3 (conflict-free, gcd(3, 32) = 1);
+// reading them straight from global memory at a 12-byte stride per thread ran at 2.0 TB/s (ncu), see profiles/.
+#define GEOM_CTA 128
+enum { S_XYZ, S_SC, S_DXYZ, S_DSC, S_MX, S_VX, S_MS, S_VS, S_POS0, S_N0, S_SLOTS };
+
+__global__ void __launch_bounds__(GEOM_CTA)
 k_adam_geom(int P, GeomArgs a, EgmAdamConst c, float nss_xyz, float nss_opacity, float nss_scaling, float nss_rotation,
             float reg_w, float reg_wn, int step) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s3[S_SLOTS][3 * GEOM_CTA];
+    const int base = blockIdx.x * GEOM_CTA;
+    const int i = base + threadIdx.x;
+    const int nv = min(GEOM_CTA, P - base) * 3;   // floats of this CTA's rows
+    const bool reg_on = reg_w > 0.f;
+    {
+        // all 30 loads of a thread are issued before the first shared-memory store (independent, fully unrolled):
+        // with a rolled loop every load waited for the previous one's store and the kernel ran latency-bound
+        const float* src[S_SLOTS] = {a.xyz, a.scaling_raw, a.d_xyz, a.d_scales, a.m_xyz, a.v_xyz, a.m_scaling,
+                                     a.v_scaling, a.pos0, a.normal0};
+        float v[S_SLOTS][3];
+#pragma unroll
+        for (int t = 0; t < S_SLOTS; t++) {
+            const bool on = t < S_POS0 || reg_on;
+            const float* g = src[t] + 3 * (size_t)base;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int j = threadIdx.x + r * GEOM_CTA;
+                v[t][r] = (on && j < nv) ? __ldg(g + j) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < S_SLOTS; t++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) s3[t][threadIdx.x + r * GEOM_CTA] = v[t][r];
+    }
+    __syncthreads();
     double acc[2] = {0.0, 0.0};   // sum |1 - cos| at the current parameters, sum (pos0 - xyz_new)^2
     if (i < P) {
+        const int l = 3 * threadIdx.x;
         EgmSurfel p, g;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            p.x[k] = a.xyz[3 * i + k]; p.s[k] = a.scaling_raw[3 * i + k];
-            g.x[k] = a.d_xyz[3 * i + k]; g.s[k] = a.d_scales[3 * i + k];
+            p.x[k] = s3[S_XYZ][l + k]; p.s[k] = s3[S_SC][l + k];
+            g.x[k] = s3[S_DXYZ][l + k]; g.s[k] = s3[S_DSC][l + k];
         }
         const float4 q4 = reinterpret_cast<const float4*>(a.rotation_raw)[i];
         const float4 g4 = reinterpret_cast<const float4*>(a.d_rotations)[i];
@@ -176,70 +266,75 @@ k_adam_geom(int P, GeomArgs a, EgmAdamConst c, float nss_xyz, float nss_opacity,
 
         // ---- activation backward + regulariser (egm_math.cuh)
         float pos0[3] = {0.f, 0.f, 0.f}, n0[3] = {0.f, 0.f, 0.f}, pos_scale = 0.f;
-        if (reg_w > 0.f) {
+        if (reg_on) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) { pos0[k] = a.pos0[3 * i + k]; n0[k] = a.normal0[3 * i + k]; }
+            for (int k = 0; k < 3; k++) { pos0[k] = s3[S_POS0][l + k]; n0[k] = s3[S_N0][l + k]; }
             const double nrm2 = a.reg[step & 1];
             pos_scale = nrm2 > 0.0 ? reg_w / (float)sqrt(nrm2) : 0.f;
         }
-        acc[0] = (double)egm_surfel_raw_grads(p, g, reg_w > 0.f, pos_scale, reg_w * reg_wn / (float)P, pos0, n0);
-        float* x = p.x; float* s = p.s; float* q = p.q;
-        const float* gx = g.x; const float* gs = g.s; const float* dq = g.q;
-        const float o = p.o, go = g.o;
-        EgmRot rot;
+        acc[0] = (double)egm_surfel_raw_grads(p, g, reg_on, pos_scale, reg_w * reg_wn / (float)P, pos0, n0);
 
-        // ---- Adam
-        float mm, vv;
+        // ---- Adam; results go back to the staging slots (S_DSC is reused for the activated scales)
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            mm = a.m_xyz[3 * i + k]; vv = a.v_xyz[3 * i + k];
-            x[k] = egm_adam_update(x[k], gx[k], mm, vv, c, nss_xyz);
-            a.m_xyz[3 * i + k] = mm; a.v_xyz[3 * i + k] = vv; a.xyz[3 * i + k] = x[k];
-            mm = a.m_scaling[3 * i + k]; vv = a.v_scaling[3 * i + k];
-            s[k] = egm_adam_update(s[k], gs[k], mm, vv, c, nss_scaling);
-            a.m_scaling[3 * i + k] = mm; a.v_scaling[3 * i + k] = vv; a.scaling_raw[3 * i + k] = s[k];
-        }
-        mm = a.m_opacity[i]; vv = a.v_opacity[i];
-        const float on = egm_adam_update(o, go, mm, vv, c, nss_opacity);
-        a.m_opacity[i] = mm; a.v_opacity[i] = vv; a.opacity_raw[i] = on;
-        float4 m4 = reinterpret_cast<const float4*>(a.m_rotation)[i], v4 = reinterpret_cast<const float4*>(a.v_rotation)[i];
-        q[0] = egm_adam_update(q[0], dq[0], m4.x, v4.x, c, nss_rotation);
-        q[1] = egm_adam_update(q[1], dq[1], m4.y, v4.y, c, nss_rotation);
-        q[2] = egm_adam_update(q[2], dq[2], m4.z, v4.z, c, nss_rotation);
-        q[3] = egm_adam_update(q[3], dq[3], m4.w, v4.w, c, nss_rotation);
-        reinterpret_cast<float4*>(a.m_rotation)[i] = m4;
-        reinterpret_cast<float4*>(a.v_rotation)[i] = v4;
-        reinterpret_cast<float4*>(a.rotation_raw)[i] = make_float4(q[0], q[1], q[2], q[3]);
-
-        // ---- activations for the next forward
-        a.opacity[i] = egm_sigmoid(on);
-#pragma unroll
-        for (int k = 0; k < 3; k++) a.scales[3 * i + k] = expf(s[k]);
-        egm_normalize_quat(q, rot);
-        reinterpret_cast<float4*>(a.rotations)[i] = make_float4(egm_nan_to_num(rot.qh[0]), egm_nan_to_num(rot.qh[1]),
-                                                                egm_nan_to_num(rot.qh[2]), egm_nan_to_num(rot.qh[3]));
-        if (reg_w > 0.f) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float d = pos0[k] - x[k];
+            float mm = s3[S_MX][l + k], vv = s3[S_VX][l + k];
+            p.x[k] = egm_adam_update(p.x[k], g.x[k], mm, vv, c, nss_xyz);
+            s3[S_MX][l + k] = mm; s3[S_VX][l + k] = vv; s3[S_XYZ][l + k] = p.x[k];
+            mm = s3[S_MS][l + k]; vv = s3[S_VS][l + k];
+            p.s[k] = egm_adam_update(p.s[k], g.s[k], mm, vv, c, nss_scaling);
+            s3[S_MS][l + k] = mm; s3[S_VS][l + k] = vv; s3[S_SC][l + k] = p.s[k];
+            s3[S_DSC][l + k] = expf(p.s[k]);
+            if (reg_on) {
+                const float d = pos0[k] - p.x[k];
                 acc[1] += (double)(d * d);
             }
         }
+        float mm = a.m_opacity[i], vv = a.v_opacity[i];
+        const float on = egm_adam_update(p.o, g.o, mm, vv, c, nss_opacity);
+        a.m_opacity[i] = mm; a.v_opacity[i] = vv; a.opacity_raw[i] = on;
+        a.opacity[i] = egm_sigmoid(on);
+        float4 m4 = reinterpret_cast<const float4*>(a.m_rotation)[i], v4 = reinterpret_cast<const float4*>(a.v_rotation)[i];
+        float q[4];
+        q[0] = egm_adam_update(p.q[0], g.q[0], m4.x, v4.x, c, nss_rotation);
+        q[1] = egm_adam_update(p.q[1], g.q[1], m4.y, v4.y, c, nss_rotation);
+        q[2] = egm_adam_update(p.q[2], g.q[2], m4.z, v4.z, c, nss_rotation);
+        q[3] = egm_adam_update(p.q[3], g.q[3], m4.w, v4.w, c, nss_rotation);
+        reinterpret_cast<float4*>(a.m_rotation)[i] = m4;
+        reinterpret_cast<float4*>(a.v_rotation)[i] = v4;
+        reinterpret_cast<float4*>(a.rotation_raw)[i] = make_float4(q[0], q[1], q[2], q[3]);
+        EgmRot rot;
+        egm_normalize_quat(q, rot);
+        reinterpret_cast<float4*>(a.rotations)[i] = make_float4(egm_nan_to_num(rot.qh[0]), egm_nan_to_num(rot.qh[1]),
+                                                                egm_nan_to_num(rot.qh[2]), egm_nan_to_num(rot.qh[3]));
     }
-    if (reg_w > 0.f) {
-        const double out[2] = {acc[0], acc[1]};
+    __syncthreads();
+    {
+        float* dst[7] = {a.xyz, a.scaling_raw, a.m_xyz, a.v_xyz, a.m_scaling, a.v_scaling, a.scales};
+        const int slot[7] = {S_XYZ, S_SC, S_MX, S_VX, S_MS, S_VS, S_DSC};
+#pragma unroll
+        for (int t = 0; t < 7; t++) {
+            float* g = dst[t] + 3 * (size_t)base;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int j = threadIdx.x + r * GEOM_CTA;
+                if (j < nv) g[j] = s3[slot[t]][j];
+            }
+        }
+    }
+    if (reg_on) {
         // slot 2: sum |1 - cos|; slot ((step + 1) & 1): next norm^2
-        __shared__ double s_part[2][4];
+        __shared__ double s_part[2][GEOM_CTA / 32];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
         for (int t = 0; t < 2; t++) {
-            const double sred = warp_sum_d(out[t]);
+            const double sred = warp_sum_d(acc[t]);
             if (lane == 0) s_part[t][warp] = sred;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const double s0 = s_part[0][0] + s_part[0][1] + s_part[0][2] + s_part[0][3];
-            const double s1 = s_part[1][0] + s_part[1][1] + s_part[1][2] + s_part[1][3];
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < GEOM_CTA / 32; wv++) { s0 += s_part[0][wv]; s1 += s_part[1][wv]; }
             if (s0 != 0.0) atomicAdd(a.reg + 2, s0);
             if (s1 != 0.0) atomicAdd(a.reg + ((step + 1) & 1), s1);
         }
@@ -305,9 +400,20 @@ EGS_API int egm_loss_seed(int32_t height, int32_t width, const float* est_color,
     // 148 SMs x 8 resident 256-thread CTAs; grid-stride beyond that
     k_mask_count<<<grid_for(n, 256 * 16, 148 * 8), 256, 0, s>>>(n, rgb_mask, geo_mask, terms);
     EGM_TRY(cudaGetLastError());
-    k_loss_seed<<<grid_for(n, 256, 148 * 8 * 4), 256, 0, s>>>(n, est_color, est_depth, est_normal, ref_color, ref_depth,
-                                                             ref_normal, rgb_mask, geo_mask, color_weight, depth_weight,
-                                                             normal_weight, dL_dcolor, dL_ddepth, dL_dnormal, terms);
+    const uintptr_t align = (uintptr_t)est_color | (uintptr_t)est_depth | (uintptr_t)est_normal | (uintptr_t)ref_color |
+                            (uintptr_t)ref_depth | (uintptr_t)ref_normal | (uintptr_t)dL_dcolor | (uintptr_t)dL_ddepth |
+                            (uintptr_t)dL_dnormal;
+    const uintptr_t malign = (uintptr_t)rgb_mask | (uintptr_t)geo_mask;
+    if (n % 4 == 0 && (align & 15) == 0 && (malign & 3) == 0)
+        k_loss_seed<4><<<grid_for(n / 4, 256, 1 << 30), 256, 0, s>>>(n, est_color, est_depth, est_normal, ref_color,
+                                                                   ref_depth, ref_normal, rgb_mask, geo_mask,
+                                                                   color_weight, depth_weight, normal_weight, dL_dcolor,
+                                                                   dL_ddepth, dL_dnormal, terms);
+    else
+        k_loss_seed<1><<<grid_for(n, 256, 1 << 30), 256, 0, s>>>(n, est_color, est_depth, est_normal, ref_color,
+                                                               ref_depth, ref_normal, rgb_mask, geo_mask, color_weight,
+                                                               depth_weight, normal_weight, dL_dcolor, dL_ddepth,
+                                                               dL_dnormal, terms);
     EGM_TRY(cudaGetLastError());
     return 0;
 }
@@ -357,7 +463,7 @@ EGS_API int egm_adam_step(int32_t P, int32_t sh_coeffs, const egm_adam* h, float
     GeomArgs a{xyz, opacity_raw, scaling_raw, rotation_raw, d_xyz, d_opacity, d_scales, d_rotations, m_xyz, v_xyz,
                m_opacity, v_opacity, m_scaling, v_scaling, m_rotation, v_rotation, pos0, normal0, reg, opacity, scales,
                rotations};
-    k_adam_geom<<<(P + 127) / 128, 128, 0, s>>>(P, a, c, nss(h->lr_xyz), nss(h->lr_opacity), nss(h->lr_scaling),
+    k_adam_geom<<<(P + GEOM_CTA - 1) / GEOM_CTA, GEOM_CTA, 0, s>>>(P, a, c, nss(h->lr_xyz), nss(h->lr_opacity), nss(h->lr_scaling),
                                                 nss(h->lr_rotation), h->reg_weight, h->reg_weight_n, h->step);
     EGM_TRY(cudaGetLastError());
     return 0;

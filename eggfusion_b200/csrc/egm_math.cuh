@@ -7,17 +7,32 @@
 #pragma once
 #include "egs_common.cuh"
 
+// Division and square root.  Device: MUFU-based approximations (div.approx / sqrt.approx, <= 2 ulp): the IEEE
+// sequences with their slow-path calls made k_adam_geom issue-bound (5100 SASS instructions, 96 CALLs per surfel;
+// 1.75 TB/s of DRAM traffic).  Host (tests/hostemu): exact, like the oracle.  Both are far inside the 1e-4 tolerance.
+#if defined(__CUDA_ARCH__)
+EGS_HD float egm_div(float a, float b) { return __fdividef(a, b); }
+EGS_HD float egm_sqrt(float a) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+#else
+EGS_HD float egm_div(float a, float b) { return a / b; }
+EGS_HD float egm_sqrt(float a) { return sqrtf(a); }
+#endif
+
 // ---- F.cosine_similarity(x1, x2, dim=-1) on 3-vectors + .clamp(-1+1e-6, 1-1e-6) + (1 - .) + abs ----------------
 // ATen: x_norm = linalg_vector_norm(x).clone(); x_norm.clamp_min_(eps) under no_grad; cos = sum((x1/x1_norm)*(x2/x2_norm)).
 // The clamp happens outside autograd, so the norm's backward still divides by the TRUE norm (0 -> masked to 0).
 // Returns |1 - clamp(cos)|; if `up` != 0 adds up * d|1 - clamp(cos)|/d x2 to dx2.
 EGS_HD float egm_cosdist(const float x1[3], const float x2[3], float up, float dx2[3]) {
     const float eps = 1e-8f;
-    const float n1t = sqrtf(x1[0] * x1[0] + x1[1] * x1[1] + x1[2] * x1[2]);
-    const float n2t = sqrtf(x2[0] * x2[0] + x2[1] * x2[1] + x2[2] * x2[2]);
+    const float n1t = egm_sqrt(x1[0] * x1[0] + x1[1] * x1[1] + x1[2] * x1[2]);
+    const float n2t = egm_sqrt(x2[0] * x2[0] + x2[1] * x2[1] + x2[2] * x2[2]);
     const float n1 = fmaxf(n1t, eps), n2 = fmaxf(n2t, eps);
-    const float a0 = x1[0] / n1, a1 = x1[1] / n1, a2 = x1[2] / n1;
-    const float b0 = x2[0] / n2, b1 = x2[1] / n2, b2 = x2[2] / n2;
+    const float a0 = egm_div(x1[0], n1), a1 = egm_div(x1[1], n1), a2 = egm_div(x1[2], n1);
+    const float b0 = egm_div(x2[0], n2), b1 = egm_div(x2[1], n2), b2 = egm_div(x2[2], n2);
     const float c = a0 * b0 + a1 * b1 + a2 * b2;
     const float lo = (float)(-1 + 1e-6), hi = (float)(1 - 1e-6);
     const float cc = fminf(fmaxf(c, lo), hi);
@@ -28,10 +43,10 @@ EGS_HD float egm_cosdist(const float x1[3], const float x2[3], float up, float d
         const float g = (c >= lo && c <= hi) ? -up * sg : 0.0f;
         // mul + sum: d/d(x2/n2) = g * (x1/n1); div: d/dx2 = . / n2, d/dn2 = -sum(. * (x2/n2) / n2)
         const float y0 = g * a0, y1 = g * a1, y2 = g * a2;
-        float e0 = y0 / n2, e1 = y1 / n2, e2 = y2 / n2;
-        const float dn2 = -(y0 * (b0 / n2) + y1 * (b1 / n2) + y2 * (b2 / n2));
+        float e0 = egm_div(y0, n2), e1 = egm_div(y1, n2), e2 = egm_div(y2, n2);
+        const float dn2 = -(y0 * egm_div(b0, n2) + y1 * egm_div(b1, n2) + y2 * egm_div(b2, n2));
         if (n2t > 0.f) {   // linalg_vector_norm backward: x * (grad / norm), masked where norm == 0
-            const float s = dn2 / n2t;
+            const float s = egm_div(dn2, n2t);
             e0 += x2[0] * s; e1 += x2[1] * s; e2 += x2[2] * s;
         }
         dx2[0] += e0; dx2[1] += e1; dx2[2] += e2;
@@ -42,17 +57,17 @@ EGS_HD float egm_cosdist(const float x1[3], const float x2[3], float up, float d
 EGS_HD float egm_sign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
 // ---- activations (gaussian_surfels.py:345-425; mapper.py:565-585) ----------------------------------------------
-EGS_HD float egm_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+EGS_HD float egm_sigmoid(float x) { return egm_div(1.0f, 1.0f + expf(-x)); }
 
 struct EgmRot {
     float qh[4];   // F.normalize(raw): raw / max(||raw||, 1e-12)
     float nq, den; // ||raw||, clamped denominator
 };
 EGS_HD void egm_normalize_quat(const float raw[4], EgmRot& r) {
-    r.nq = sqrtf(raw[0] * raw[0] + raw[1] * raw[1] + raw[2] * raw[2] + raw[3] * raw[3]);
+    r.nq = egm_sqrt(raw[0] * raw[0] + raw[1] * raw[1] + raw[2] * raw[2] + raw[3] * raw[3]);
     r.den = fmaxf(r.nq, 1e-12f);
 #pragma unroll
-    for (int i = 0; i < 4; i++) r.qh[i] = raw[i] / r.den;
+    for (int i = 0; i < 4; i++) r.qh[i] = egm_div(raw[i], r.den);
 }
 // Mapper.total_params: rotations = torch.nan_to_num(get_rotation, nan=1.0) (+-inf -> +-FLT_MAX)
 EGS_HD float egm_nan_to_num(float x) {
@@ -68,12 +83,12 @@ EGS_HD void egm_normalize_quat_bwd(const float raw[4], const EgmRot& r, const fl
     float dden = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        draw[i] = dqh[i] / r.den;
-        dden -= dqh[i] * (r.qh[i] / r.den);
+        draw[i] = egm_div(dqh[i], r.den);
+        dden -= dqh[i] * egm_div(r.qh[i], r.den);
     }
     // clamp_min backward: grad * (norm >= eps); norm backward: x * (grad / norm), masked where norm == 0
     if (r.nq >= 1e-12f && r.nq > 0.f) {
-        const float s = dden / r.nq;
+        const float s = egm_div(dden, r.nq);
 #pragma unroll
         for (int i = 0; i < 4; i++) draw[i] += raw[i] * s;
     }
@@ -96,9 +111,9 @@ EGS_HD int egm_argmin3(float a, float b, float c) {   // torch.argmin: first min
 }
 EGS_HD void egm_get_normal(const float qh[4], int k, EgmNormal& s, float n[3]) {
     s.k = k;
-    s.nb = sqrtf(qh[0] * qh[0] + qh[1] * qh[1] + qh[2] * qh[2] + qh[3] * qh[3]);
+    s.nb = egm_sqrt(qh[0] * qh[0] + qh[1] * qh[1] + qh[2] * qh[2] + qh[3] * qh[3]);
 #pragma unroll
-    for (int i = 0; i < 4; i++) s.q[i] = qh[i] / s.nb;
+    for (int i = 0; i < 4; i++) s.q[i] = egm_div(qh[i], s.nb);
     const float r = s.q[0], x = s.q[1], y = s.q[2], z = s.q[3];
     if (k == 0) {
         s.v[0] = 1 - 2 * (y * y + z * z); s.v[1] = 2 * (x * y + r * z); s.v[2] = 2 * (x * z - r * y);
@@ -107,9 +122,9 @@ EGS_HD void egm_get_normal(const float qh[4], int k, EgmNormal& s, float n[3]) {
     } else {
         s.v[0] = 2 * (x * z + r * y); s.v[1] = 2 * (y * z - r * x); s.v[2] = 1 - 2 * (x * x + y * y);
     }
-    s.mag = sqrtf(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
+    s.mag = egm_sqrt(s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2]);
     const float d = s.mag + 1e-8f;
-    n[0] = s.v[0] / d; n[1] = s.v[1] / d; n[2] = s.v[2] / d;
+    n[0] = egm_div(s.v[0], d); n[1] = egm_div(s.v[1], d); n[2] = egm_div(s.v[2], d);
 }
 // dL/dn -> adds dL/dqh (gradient w.r.t. the F.normalize output that build_rotation received)
 EGS_HD void egm_get_normal_bwd(const float qh[4], const EgmNormal& s, const float dn[3], float dqh[4]) {
@@ -118,11 +133,11 @@ EGS_HD void egm_get_normal_bwd(const float qh[4], const EgmNormal& s, const floa
     float dmag = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        dv[i] = dn[i] / d;
-        dmag -= dn[i] * ((s.v[i] / d) / d);
+        dv[i] = egm_div(dn[i], d);
+        dmag -= dn[i] * egm_div(egm_div(s.v[i], d), d);
     }
     if (s.mag > 0.f) {
-        const float t = dmag / s.mag;
+        const float t = egm_div(dmag, s.mag);
 #pragma unroll
         for (int i = 0; i < 3; i++) dv[i] += s.v[i] * t;
     }
@@ -147,9 +162,9 @@ EGS_HD void egm_get_normal_bwd(const float qh[4], const EgmNormal& s, const floa
     // q = qh / nb with nb = sqrt(sum qh^2)
     float dnb = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) dnb -= dq[i] * (s.q[i] / s.nb);
+    for (int i = 0; i < 4; i++) dnb -= dq[i] * egm_div(s.q[i], s.nb);
 #pragma unroll
-    for (int i = 0; i < 4; i++) dqh[i] += dq[i] / s.nb + dnb * (qh[i] / s.nb);
+    for (int i = 0; i < 4; i++) dqh[i] += egm_div(dq[i], s.nb) + dnb * egm_div(qh[i], s.nb);
 }
 
 // ---- one surfel: gradients w.r.t. the ACTIVATED parameters -> gradients w.r.t. the raw parameters (+ regulariser) ----
@@ -196,6 +211,6 @@ struct EgmAdamConst {
 EGS_HD float egm_adam_update(float p, float g, float& m, float& v, const EgmAdamConst& c, float neg_step_size) {
     m = m + c.one_m_beta1 * (g - m);              // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5 branch
     v = v * c.beta2 + c.one_m_beta2 * g * g;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-    return p + neg_step_size * (m / denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
+    const float denom = egm_div(egm_sqrt(v), c.bc2_sqrt) + c.eps;
+    return p + neg_step_size * egm_div(m, denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
 }

@@ -69,6 +69,24 @@ def test_loss_edge_cases():
                     torch.ones(4, 4, dtype=torch.bool), None, w)
 
 
+def test_loss_scalar_path_on_odd_image_size():
+    """H*W not a multiple of 4 (and unaligned views) takes the one-pixel-per-thread kernel; same numbers."""
+    from eggfusion_b200 import mapping as M
+    raw, its, (cw, dw, nw, rw, rwn), lr = mg.case_inputs("mapping_deg3")
+    it = its[1]
+    c = lambda a, hwc: np.ascontiguousarray(a[:39, :55] if hwc else a[:, :39, :55])
+    args = (c(it["est_color"], 0), c(it["est_depth"], 0), c(it["est_normal"], 0), c(it["ref_color"], 1),
+            c(it["ref_depth"], 1), c(it["ref_normal"], 1), c(it["rgb_mask"], 1), c(it["geo_mask"], 1))
+    w = M.MappingWeights(cw, dw, nw)
+    terms, gc, gd, gn = M.loss_seed(*[t(a) for a in args], w)
+    o = mo.loss_seed(*args, cw, dw, nw)
+    out = n(M.loss_total(terms, w))
+    assert int(n(terms)[0]) == o["count"]
+    assert abs(out[0] - o["image_loss"]) <= 1e-5 * abs(o["image_loss"])
+    for got, key in ((gc, "dL_dcolor"), (gd, "dL_ddepth"), (gn, "dL_dnormal")):
+        assert rel_err(n(got), o[key]) <= 1e-5, key
+
+
 def _forced_optimizer(M, name, gold, k, raw0, weights, lr):
     """FrameBatchOptimizer holding the reference's parameters / Adam state after iteration k-1 (each step on its own)."""
     opt = M.FrameBatchOptimizer({nm: t(raw0[nm]) for nm in NAMES}, M.LrParams(**lr), weights)
