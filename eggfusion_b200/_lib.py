@@ -58,6 +58,22 @@ SIGNATURES.update({
     "egt_solve_block": (C.c_int, [_P, _P, C.c_float, _P, _I32, _P]),
 })
 
+
+class Level(C.Structure):
+    """struct egt_level"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("model_disp", C.c_void_p), ("model_vertex", C.c_void_p),
+                ("model_normal", C.c_void_p), ("model_mask", C.c_void_p), ("model_intensity", C.c_void_p),
+                ("frame_vertex", C.c_void_p), ("frame_normal", C.c_void_p), ("frame_mask", C.c_void_p),
+                ("frame_intensity", C.c_void_p), ("frame_grad", C.c_void_p)]
+
+
+EGT_GN_SUMS = 56
+SIGNATURES.update({
+    "egt_gn_accumulate": (C.c_int, [C.POINTER(Level), _P, C.c_float, C.c_float, _I32, _P, _P]),
+    "egt_gn_solve_update": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
+})
+
 # include/eggmap.h
 class AdamHyper(C.Structure):
     """struct egm_adam"""

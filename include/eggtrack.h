@@ -13,6 +13,11 @@
  *   egt_compute_gradients     gradient_kernel                TRK:853-926   (live: frame.py:72,97, system.py:92)
  *   egt_vertex_normal_map     compute_vertex/normal_map_kernel TRK:602-702 (live: frame.py:42, mapper.py:260)
  *   egt_solve_block           solveBlock (CPU Eigen QR)      TRK:929-950   (live: tracker.py:238)
+ *   egt_gn_accumulate         Tracker.tracking_optimization, first half (src/core/tracker.py:194-227): the PyTorch
+ *                             functions projective_transform (src/core/optimizer.py:131-180), icp_optimization
+ *                             (:317-377) and rgb_optimization (:278-315) fused into one pass        
+ *   egt_gn_solve_update       second half (tracker.py:229-251): combine, solve_block, convergence test, and
+ *                             update_transform (optimizer.py:426-441) applied to the pose on the device
  * The three remaining exports of the reference (projective_transform / rgb_optimization / icp_optimization) are
  * dead or non-functional there and are not part of this ABI.
  */
@@ -49,6 +54,38 @@ EGS_API int egt_vertex_normal_map(const float* depth, float fx, float fy, float 
 /* x = solve((A + lm I) x = b) for one dense n x n system, n <= 16, entirely on the device (A row- or column-major:
  * the tracker's A is symmetric).  Singular systems yield zeros. */
 EGS_API int egt_solve_block(const float* A, const float* b, float lm, float* x, int32_t n, void* stream);
+
+/* One pyramid level of the model (rendered, "prev"/frame1) and of the incoming frame ("curr"/frame2), PyraImageCUDA
+ * layout (src/utils/frame.py:20-99): row-major [height][width][C] float32, masks bool [height][width]. */
+typedef struct egt_level {
+    int32_t width, height;
+    float fx, fy, cx, cy;            /* intrinsic_pyramid[level] */
+    const float* model_disp;         /* disp_pyramid      [h][w][1] */
+    const float* model_vertex;       /* vertex_pyramid    [h][w][3] */
+    const float* model_normal;       /* normal_pyramid    [h][w][3] */
+    const uint8_t* model_mask;       /* mask_pyramid      [h][w][1] */
+    const float* model_intensity;    /* intensity_pyramid [h][w][1] (rgb term only) */
+    const float* frame_vertex;
+    const float* frame_normal;
+    const uint8_t* frame_mask;
+    const float* frame_intensity;    /* (rgb term only) */
+    const float* frame_grad;         /* grad_pyramid [h][w][3] = d/dx, d/dy, magnitude (rgb term only) */
+} egt_level;
+
+/* sums (device double[EGT_GN_SUMS]): [0,21) upper triangle of J^T J of the ICP term (row-major: 00 01 .. 05 11 ..),
+ * [21,27) its J^T r, [27] its valid-pixel count; [28,56) the same for the photometric term. */
+#define EGT_GN_SUMS 56
+
+/* transform: device float[16], row-major 4x4 (the current dense_delta).  Zeroes `sums`, then accumulates. */
+EGS_API int egt_gn_accumulate(const egt_level* level, const float* transform, float angle_thres_deg, float dist_thres,
+                              int32_t use_rgb, double* sums, void* stream);
+
+/* A = A_icp + rgb_weight A_rgb, b likewise; dx = solve((A + lm I) dx = b); converged = ||b|| / max(1, sqrt(count)) <
+ * residual_thres && ||dx|| < dx_thres; transform <- update_transform(transform, dx) in place.
+ * dx_out: float[6] or NULL; system_out: float[42] = A (row-major 6x6) then b, or NULL;
+ * status: int32[4] or NULL: [0] |= converged (caller zeroes it per frame), [1] converged, [2] icp count, [3] rgb count. */
+EGS_API int egt_gn_solve_update(const double* sums, float rgb_weight, float lm, float residual_thres, float dx_thres,
+                                float* transform, float* dx_out, float* system_out, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }
