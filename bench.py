@@ -298,6 +298,152 @@ def reference_mapping_iteration_factory(rast_mod, raw, frames, settings, deg):
     return iteration, losses
 
 
+# ------------------------------------------------------------------------------------------------ dense tracking
+TRACK_CFG = dict(pyramid_level=3, pyramid_iters=(3, 3, 3), angle_threshold=20.0, distance_threshold=0.1, use_rgb=True,
+                 rgb_weight=1e-4, residual_thres=0.01, dx_threshold=0.001)      # configs/replica/base.yaml:29-37
+
+
+def tracking_inputs(dev, W=1200, H=680, levels=3):
+    """Model / frame pyramids (PyraImageCUDA attribute lists) of a smooth synthetic surface at the Replica frame size
+    (configs/replica/base.yaml:4-16) + an initial pose 5 mm / 0.2 deg off."""
+    import types
+    import torch
+    r = np.random.default_rng(31)
+    fx = fy = 600.0
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+
+    def maps(phase):
+        z = 2.0 + 0.3 * np.sin(xx / W * 5 + phase) * np.cos(yy / H * 4) + 0.002 * r.standard_normal((H, W))
+        v = np.stack([(xx - cx) / fx * z, (yy - cy) / fy * z, z], -1)
+        nrm = np.cross(np.gradient(v, axis=0), np.gradient(v, axis=1))
+        nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+        I = 0.5 + 0.4 * np.sin(xx * 0.9 + phase) * np.cos(yy * 0.7) + 0.05 * r.standard_normal((H, W))
+        gx_, gy_ = np.gradient(I, axis=1) * 8, np.gradient(I, axis=0) * 8
+        grad = np.stack([gx_, gy_, np.sqrt(gx_ ** 2 + gy_ ** 2 + 1e-6)], -1)
+        return {"vertex": v, "normal": nrm, "intensity": I[..., None], "grad": grad,
+                "mask": r.uniform(0, 1, (H, W, 1)) < 0.95, "disp": 1.0 / (z[..., None] + 1e-6)}
+
+    def pyr(m):
+        out = {k + "_pyramid": [] for k in m}
+        out["intrinsic_pyramid"] = []
+        for l in range(levels):
+            sc = 2 ** l
+            for k, v in m.items():
+                a = np.ascontiguousarray(v[::sc, ::sc])
+                out[k + "_pyramid"].append(torch.from_numpy(a if a.dtype == bool else a.astype(np.float32)).to(dev))
+            out["intrinsic_pyramid"].append(torch.tensor([fx / sc, fy / sc, cx / sc, cy / sc]))
+        return types.SimpleNamespace(**out)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = [0.003, -0.004, 0.002]
+    c, s_ = np.cos(0.0035), np.sin(0.0035)
+    T[:3, :3] = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]], np.float32)
+    return pyr(maps(0.0)), pyr(maps(0.01)), torch.from_numpy(T).to(dev)
+
+
+def reference_tracking_frame_factory(model, frame, T0):
+    """The dense part of Tracker.tracking_frame (/root/reference/src/core/tracker.py:153-169) as the reference runs it:
+    per Gauss-Newton step projective_transform (optimizer.py:131-180), icp_optimization (:317-377),
+    rgb_optimization (:278-315) in PyTorch, solve_block on the CPU (src/utils/cuda/src/tracking.cu:929-950: A and b go
+    to the host, QR there, x comes back), the .item() convergence test (tracker.py:235-250) and update_transform
+    (optimizer.py:426-441).  Plain torch ops restated here because /root/reference is not on the GPU box."""
+    import math
+    import torch
+    import torch.nn.functional as F
+    cfg = TRACK_CFG
+
+    def projective_transform(transform, disps, intr):
+        grid = torch.stack(torch.meshgrid(torch.arange(disps.shape[0]), torch.arange(disps.shape[1]), indexing="ij"),
+                           dim=-1).to(transform.device)
+        ht, wd = grid.shape[:2]
+        fx, fy, cx, cy = intr
+        grid_y, grid_x = torch.unbind(grid, dim=-1)
+        I, O = torch.ones_like(grid_x), torch.zeros_like(grid_x)
+        us, vs = (grid_x - cx) / fx, (grid_y - cy) / fy
+        Ps = torch.stack([us, vs, I, disps.squeeze()], dim=-1).to(transform.device)
+        Pt = (Ps.reshape(-1, 4) @ transform.T).reshape(ht, wd, 4)
+        ut, vt, zt, dt = torch.unbind(Pt, dim=-1)
+        ut, vt, dt = ut / zt, vt / zt, dt / zt
+        dxdxi = torch.stack([dt * fx, O, -ut * dt * fx, -ut * vt * fx, (1 + ut * ut) * fx, -vt * fx,
+                             O, dt * fy, -vt * dt * fy, -(1 + vt * vt) * fy, ut * vt * fy, ut * fy],
+                            dim=-1).reshape(ht, wd, 2, 6)
+        wg = torch.stack([fx * ut + cx, fy * vt + cy], dim=-1).to(grid.device)
+        wg[..., 0] = 2 * wg[..., 0] / (wd - 1) - 1
+        wg[..., 1] = 2 * wg[..., 1] / (ht - 1) - 1
+        return wg, dxdxi
+
+    def inside(coords, bound):
+        return ((coords[..., 0] > -bound) & (coords[..., 0] < bound) & (coords[..., 1] > -bound)
+                & (coords[..., 1] < bound)).reshape(-1, 1)
+
+    def icp(level, T, coords):
+        vprev = model.vertex_pyramid[level].reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]
+        nprev = model.normal_pyramid[level].reshape(-1, 3) @ T[:3, :3].T
+        gs = lambda m: F.grid_sample(m.permute(2, 0, 1)[None], coords[None], mode="nearest", padding_mode="border",
+                                     align_corners=True)[0].permute([1, 2, 0]).reshape(-1, 3)
+        vcurr, ncurr = gs(frame.vertex_pyramid[level]), gs(frame.normal_pyramid[level])
+        delta_v = vcurr - vprev
+        cross_n = torch.cross(ncurr, nprev, dim=1)
+        dist, sine = torch.norm(delta_v, dim=-1), torch.norm(cross_n, dim=-1)
+        nan_mask = ~torch.isnan(cross_n)
+        nan_mask = (nan_mask[..., 0] & nan_mask[..., 1] & nan_mask[..., 2]).reshape(-1, 1)
+        pos_mask = (vprev[..., -1] > 0).reshape(-1, 1)
+        valid = ((sine < cfg["angle_threshold"] * math.pi / 180) & (dist < cfg["distance_threshold"])).reshape(-1, 1)
+        weight = (nan_mask & inside(coords, 0.98) & pos_mask & valid & model.mask_pyramid[level].reshape(-1, 1)
+                  & frame.mask_pyramid[level].reshape(-1, 1))
+        r = torch.sum(ncurr * delta_v, dim=1).reshape(-1, 1)
+        J = torch.cat([ncurr, torch.cross(vprev, ncurr, dim=1)], dim=1)
+        J, r = J[weight.squeeze()], r[weight.squeeze()]
+        return torch.matmul(J.T, J), torch.matmul(J.T, r), int(weight.sum().item())
+
+    def rgb(level, coords, Jc):
+        grad_mask = (frame.grad_pyramid[level][..., 2] > 1).reshape(-1, 1)
+        mask_prev = model.mask_pyramid[level].reshape(-1, 1)
+        model_I = model.intensity_pyramid[level].permute([2, 0, 1])[None]
+        frame_I = frame.intensity_pyramid[level].permute([2, 0, 1])[None]
+        sample_I = F.grid_sample(frame_I, coords[None], mode="bilinear", padding_mode="zeros", align_corners=True)
+        Ji = F.grid_sample(frame.grad_pyramid[level][..., :2].permute([2, 0, 1])[None], coords[None], mode="bilinear",
+                           padding_mode="zeros", align_corners=True).permute([2, 3, 0, 1])
+        mask_curr = F.grid_sample(frame.mask_pyramid[level].permute([2, 0, 1])[None].float(), coords[None],
+                                  mode="nearest", padding_mode="zeros", align_corners=True).permute([2, 3, 0, 1])
+        mask_curr = (mask_curr > 0.8).reshape(-1, 1)
+        weight = inside(coords, 0.90) & mask_prev & grad_mask & mask_curr
+        J = torch.matmul(Ji, Jc).reshape(-1, 6)
+        r = (model_I - sample_I).reshape(-1, 1)
+        J, r = J[weight.squeeze()], r[weight.squeeze()]
+        return torch.matmul(J.T, J), torch.matmul(J.T, r), int(weight.sum().item())
+
+    def so3_exp(theta):
+        W = torch.tensor([[0, -theta[2], theta[1]], [theta[2], 0, -theta[0]], [-theta[1], theta[0], 0]],
+                         device=theta.device, dtype=theta.dtype)
+        angle = torch.norm(theta)
+        I = torch.eye(3, device=theta.device, dtype=theta.dtype)
+        return torch.where(angle < 1e-5, I + W + 0.5 * W @ W,
+                           I + (torch.sin(angle) / angle) * W + ((1 - torch.cos(angle)) / (angle ** 2)) * W @ W)
+
+    def track(_i):
+        dense = T0.clone()
+        conv_any = False
+        for l in range(cfg["pyramid_level"]):
+            for _ in range(cfg["pyramid_iters"][l]):
+                level = cfg["pyramid_level"] - 1 - l
+                coords, Jc = projective_transform(dense, model.disp_pyramid[level], model.intrinsic_pyramid[level])
+                A_i, b_i, n_i = icp(level, dense, coords)
+                A_r, b_r, n_r = rgb(level, coords, Jc)
+                A, b = A_i + cfg["rgb_weight"] * A_r, b_i + cfg["rgb_weight"] * b_r
+                A_cpu, b_cpu = A.float().cpu(), b.float().cpu()                       # solveBlock: GPU -> CPU
+                x = torch.linalg.lstsq(A_cpu + 1e-6 * torch.eye(6), b_cpu).solution    # (Eigen colPivHouseholderQr there)
+                dx = x.to(A.device).reshape(-1)
+                res_norm = float(torch.norm(b).item())
+                residual_est = res_norm / max(1.0, (n_i + n_r) ** 0.5)
+                dx_norm = float(torch.norm(dx).item())
+                conv_any = conv_any or ((residual_est < cfg["residual_thres"]) and (dx_norm < cfg["dx_threshold"]))
+                dense[:3, :3] = so3_exp(dx[3:]) @ dense[:3, :3]
+                dense[:3, 3] = dx[:3] + dense[:3, 3]
+        return dense, conv_any
+    return track
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_baseline_sample(scene, cams, grads, deg, budget_s=12.0):
     """Oracle port (C, OpenMP, all host cores) on a bounded sample of the same workload: whole frames (forward +
@@ -512,6 +658,22 @@ def run_ours(args):
                            "ms_per_iter_loss_item_each_iter: blocking loss.item() every iteration like the reference loop",
                    "gpu_launches_per_iter": 7 + 2 + 1 + 2}
         del fm, mopt
+    tracking = None
+    if world == 1 and not args.no_tracking:
+        from eggfusion_b200 import tracking as TRK
+        pm, pf, T0 = tracking_inputs(dev)
+        trk = TRK.DenseTracker(TRK.TrackingConfig(**TRACK_CFG), dev)
+        eye = torch.eye(4, device=dev)
+        last = {}
+
+        def trk_frame(i):
+            last["T"], last["conv"] = trk.track(pm, pf, T0, eye)
+        ms_trk = time_loop(trk_frame, max(3, args.warmup), args.steps)
+        tracking = {"ms_per_frame": ms_trk, "frames_per_s": 1e3 / ms_trk, "converged": bool(last["conv"]),
+                    "dense_delta_t": [float(v) for v in trk.last_dense_delta[:3, 3]],
+                    "what": "dense part of Tracker.tracking_frame: 9 Gauss-Newton steps over a 3-level 1200x680 pyramid "
+                            "(eggfusion_b200.tracking.DenseTracker.track: 2 launches per step, no host sync)",
+                    "gpu_launches_per_frame": 9 * 3}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -557,6 +719,7 @@ def run_ours(args):
         "gpu_launches": 7 * args.steps * world,
         "e2e": e2e,
         "mapping_iter": mapping,
+        "tracking_frame": tracking,
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)
@@ -683,6 +846,19 @@ def run_reference(args):
                    "what": "one Mapper.frame_batch_optimization iteration with the reference rasterizer and the "
                            "reference's torch glue (activations, compute_loss incl. check_nan, backward, torch Adam, "
                            "loss.item())"}
+    tracking = None
+    if not args.no_tracking:
+        pm, pf, T0 = tracking_inputs(dev)
+        track = reference_tracking_frame_factory(pm, pf, T0)
+        last = {}
+
+        def trk_frame(i):
+            last["T"], last["conv"] = track(i)
+        ms_trk = time_loop(trk_frame, max(3, args.warmup), max(5, args.steps // 5))
+        tracking = {"ms_per_frame": ms_trk, "frames_per_s": 1e3 / ms_trk, "converged": bool(last["conv"]),
+                    "dense_delta_t": [float(v) for v in last["T"][:3, 3]],
+                    "what": "dense part of Tracker.tracking_frame with the reference's PyTorch flow (projective_transform, "
+                            "icp_optimization, rgb_optimization, CPU solve, .item() convergence test)"}
     line = {
         "impl": "reference", "device": "cuda (unmodified diff-gaussian-surfels compiled for sm_100a, oracle/_ref)",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -699,6 +875,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 4 + 4 + 8 * 8160,
                 "api": "diff_gaussian_rasterization.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"},
         "mapping_iter": mapping,
+        "tracking_frame": tracking,
     }
     print(json.dumps(line))
 
@@ -713,6 +890,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mapping", action="store_true")
+    ap.add_argument("--no-tracking", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

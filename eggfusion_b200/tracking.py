@@ -107,5 +107,6 @@ class DenseTracker:
             for _ in range(cfg.pyramid_iters[l]):
                 self.tracking_optimization(model, frame, level, dense_delta, _lv=levels[level])
         conv = self.status[0] != 0
+        self.last_dense_delta = dense_delta   # the optimised delta, whether or not it is committed
         curr = torch.where(conv, dense_delta @ prev_transform, delta_transform @ prev_transform)
         return curr, conv
