@@ -72,6 +72,8 @@ EGT_GN_SUMS = 56
 SIGNATURES.update({
     "egt_gn_accumulate": (C.c_int, [C.POINTER(Level), _P, C.c_float, C.c_float, _I32, _P, _P]),
     "egt_gn_solve_update": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
+    "egt_track_pyramid": (C.c_int, [_P, _I32, _P, C.c_float, C.c_float, _I32, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, _P, _P, _P, _P, _P, _P]),
 })
 
 # include/eggmap.h

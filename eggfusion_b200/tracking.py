@@ -98,14 +98,15 @@ class DenseTracker:
         dense_converged [] bool), both on the device; nothing is read back."""
         cfg = self.cfg
         dense_delta = delta_transform.detach().clone().float().contiguous()
-        self.status.zero_()
-        levels = {}
-        for l in range(cfg.pyramid_level):
-            level = cfg.pyramid_level - 1 - l
-            if level not in levels:
-                levels[level] = make_level(model, frame, level)
-            for _ in range(cfg.pyramid_iters[l]):
-                self.tracking_optimization(model, frame, level, dense_delta, _lv=levels[level])
+        made = [make_level(model, frame, level) for level in range(cfg.pyramid_level)]
+        levels = (_lib.Level * cfg.pyramid_level)(*[m[0] for m in made])
+        iters = (C.c_int32 * cfg.pyramid_level)(*[int(v) for v in cfg.pyramid_iters[:cfg.pyramid_level]])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.egt_track_pyramid(levels, cfg.pyramid_level, iters, cfg.angle_threshold,
+                                                  cfg.distance_threshold, int(cfg.use_rgb), cfg.rgb_weight, cfg.lm,
+                                                  cfg.residual_thres, cfg.dx_threshold, dense_delta.data_ptr(),
+                                                  self.sums.data_ptr(), self.dx.data_ptr(), self.system.data_ptr(),
+                                                  self.status.data_ptr(), R._stream_ptr(self.device)), "track_pyramid")
         conv = self.status[0] != 0
         self.last_dense_delta = dense_delta   # the optimised delta, whether or not it is committed
         curr = torch.where(conv, dense_delta @ prev_transform, delta_transform @ prev_transform)

@@ -16,6 +16,7 @@
  *   egt_gn_accumulate         Tracker.tracking_optimization, first half (src/core/tracker.py:194-227): the PyTorch
  *                             functions projective_transform (src/core/optimizer.py:131-180), icp_optimization
  *                             (:317-377) and rgb_optimization (:278-315) fused into one pass        
+ *   egt_track_pyramid         the whole coarse-to-fine loop of Tracker.tracking_frame (tracker.py:153-164) in one call
  *   egt_gn_solve_update       second half (tracker.py:229-251): combine, solve_block, convergence test, and
  *                             update_transform (optimizer.py:426-441) applied to the pose on the device
  * The three remaining exports of the reference (projective_transform / rgb_optimization / icp_optimization) are
@@ -86,6 +87,14 @@ EGS_API int egt_gn_accumulate(const egt_level* level, const float* transform, fl
  * status: int32[4] or NULL: [0] |= converged (caller zeroes it per frame), [1] converged, [2] icp count, [3] rgb count. */
 EGS_API int egt_gn_solve_update(const double* sums, float rgb_weight, float lm, float residual_thres, float dx_thres,
                                 float* transform, float* dx_out, float* system_out, int32_t* status, void* stream);
+
+/* The dense loop of Tracker.tracking_frame (tracker.py:153-164) in ONE call: for l in 0..nlevel-1, iters[l] Gauss-Newton
+ * steps on pyramid level nlevel-1-l (levels[] is indexed by pyramid level), each = egt_gn_accumulate + egt_gn_solve_update
+ * on `transform` (device, in/out).  status[0] = any step converged.  2 launches per step, no host involvement. */
+EGS_API int egt_track_pyramid(const egt_level* levels, int32_t nlevel, const int32_t* iters, float angle_thres_deg,
+                              float dist_thres, int32_t use_rgb, float rgb_weight, float lm, float residual_thres,
+                              float dx_thres, float* transform, double* sums, float* dx_out, float* system_out,
+                              int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }
