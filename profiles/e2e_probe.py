@@ -9,7 +9,7 @@ from eggfusion_b200 import rasterizer as R
 R.config.capacity = sys.argv[1] if len(sys.argv) > 1 else "exact"
 print("capacity policy:", R.config.capacity)
 dev = torch.device("cuda", 0)
-scene, cams, grads, deg = bench.make_workload("C3")
+scene, cams, grads, deg = bench.make_workload(sys.argv[2] if len(sys.argv) > 2 else "C3")
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 params = {k: t(scene[k]) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
 leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}

@@ -394,6 +394,8 @@ def _random_case(seed, P, W, H, deg, layers=3, big=False, dense_tile=False):
     (103, 1200, 130, 70, 1, {"big": True}),           # huge splats
     (104, 9000, 48, 48, 0, {"dense_tile": True}),     # > 4096 instances in one tile: global-memory sort path
     (105, 2500, 320, 200, 3, {"layers": 6}),
+    (106, 40000, 1200, 680, 3, {}),                   # BASELINE config C2 frame (Replica 1200x680, SH degree 3)
+    (107, 30000, 640, 480, 0, {}),                    # BASELINE config C5 frame (TUM 640x480, SH degree 0)
 ])
 def test_fuzz_against_oracle(seed, P, W, H, deg, kw):
     import eggfusion_b200 as E
