@@ -19,7 +19,7 @@ if [ "$1" = build ]; then
 else
   for so in "$V"/libeggsplat_*.so; do
     n=$(basename "$so" .so); n=${n#libeggsplat_}
-    EGS_LIB=$so python "$ROOT/bench.py" --steps 40 --warmup 5 --no-cpu --no-e2e 2>/dev/null | tail -1 | \
+    EGS_LIB=$so python "$ROOT/bench.py" --steps 60 --warmup 5 --no-cpu --no-e2e --no-mapping --no-tracking 2>/dev/null | tail -1 | \
       python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$n', round(d['ms_per_step'],4), {k: round(v,4) for k,v in d['stage_ms'].items()})"
   done
 fi

@@ -369,6 +369,31 @@ def test_backward_kernel_variants_agree():
     assert rel_err(outs["warp"], sg) <= TOL
 
 
+def test_forward_tma_variant_is_bit_identical():
+    """EGS_FWD_KERNEL=bulk (records staged by cp.async.bulk / mbarrier, double-buffered) performs the same arithmetic
+    in the same order as the default forward: images, saved state and the screen gradients that the backward derives
+    from its hit lists must be identical."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_parity_gpu as T\n"
+        "o = T.cuda_run(sys.argv[2])\n"
+        "np.savez(sys.argv[1], color=o['color'], depth=o['depth'], normal=o['normal_img'], opacity=o['opacity'],\n"
+        "         n_contrib=o['n_contrib'], final_T=o['final_T'], g=o['g_screen'])\n"
+    ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
+    for case in ("c1_posed_bg", "small_deg0_ragged"):
+        outs = {}
+        for variant in ("ldg", "bulk"):
+            path = "/tmp/egs_fwd_%s.npz" % variant
+            env = dict(os.environ, EGS_FWD_KERNEL=variant)
+            subprocess.run([sys.executable, "-c", code, path, case], check=True, env=env, cwd=util.ROOT)
+            outs[variant] = np.load(path)
+        for k in ("color", "depth", "normal", "opacity", "n_contrib", "final_T"):
+            assert np.array_equal(outs["ldg"][k], outs["bulk"][k]), (case, k)
+        assert rel_err(outs["bulk"]["g"], outs["ldg"]["g"]) <= 2e-6, case      # float atomics: order differs run to run
+
+
 def _random_case(seed, P, W, H, deg, layers=3, big=False, dense_tile=False):
     """Seeded random scene + posed camera + gradients for the fuzz tests."""
     from eggfusion_b200 import synthetic as syn
