@@ -1,5 +1,6 @@
 // egs_preprocess.cu -- per-surfel kernels: forward projection (+ per-tile instance counting), per-surfel backward,
-// and the coarse visibility test.  One thread per surfel, 128-thread CTAs (the SH blocks live in registers), per-frame constants staged in smem.
+// and the coarse visibility test.  One thread per surfel, 128-thread CTAs; the CTA's SH block and the per-frame
+// constants are staged in shared memory.
 //
 // Replaces preprocessCUDA<3> (DGS/cuda_rasterizer/forward.cu:158-301), computeCov2DCUDA + preprocessCUDA<3> (bwd)
 // (DGS/cuda_rasterizer/backward.cu:144-416) and checkFrustum (DGS/cuda_rasterizer/rasterizer_impl.cu:54-66).

@@ -8,10 +8,11 @@
 //   solve_block          (src/utils/cuda/src/tracking.cu:929-950: GPU -> CPU Eigen QR -> GPU)
 //   4 x .item() for the convergence test, update_transform (optimizer.py:426-441)
 // ~70 launches and 7 host round trips per step, 9 steps per frame.  Here: k_gn_accumulate makes ONE pass over the
-// level's pixels (every map read once, Jacobian rows live in registers, the 2 x (21 + 6) sums + 2 counts are reduced
-// in registers -> shuffles -> one double atomic per CTA and value), k_gn_solve_update (one thread) combines the terms,
-// solves the 6x6 system, evaluates the convergence test and applies update_transform to the pose ON THE DEVICE, so
-// the whole pyramid loop runs without a host sync.  HBM-bound streaming: ~120 B per pixel.
+// level's pixels (every map read once, Jacobian rows live in registers; the 2 x (21 + 6) sums + 2 counts are reduced
+// by a transposing warp reduction -> one running scalar per lane -> shared memory -> one double atomic per CTA and
+// value), k_gn_solve_update (one thread) combines the terms, solves the 6x6 system, evaluates the convergence test and
+// applies update_transform to the pose ON THE DEVICE; egt_track_pyramid enqueues the whole coarse-to-fine loop
+// (2 launches per step) without a host sync.  HBM-bound streaming: ~120 B per pixel.
 #include "egs_common.cuh"
 #include "../../include/eggtrack.h"
 
@@ -19,10 +20,6 @@ namespace {
 
 #define GN_CTA 128
 #define GN_SUMS 56   // icp: 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (count); rgb: the same
-
-struct Pose {
-    float m[16];
-};
 
 // F.grid_sample(align_corners=True): [-1, 1] -> [0, size - 1]
 __device__ __forceinline__ float unnormalize(float g, int size) { return (g + 1.f) * 0.5f * (float)(size - 1); }
