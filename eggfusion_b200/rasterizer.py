@@ -59,7 +59,13 @@ def _present(t: Optional[torch.Tensor]) -> bool:
     return t is not None and t.numel() > 0
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device) -> int:
+    """cudaStream_t of torch's current stream on `device` (the raw getter skips building a Stream object)."""
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -127,10 +133,20 @@ def make_frame(P: int, settings: GaussianRasterizationSettings, sh_coeffs: int, 
     return fr, (bg, view, proj, campos)
 
 
+_ws_cache = {}
+
+
 def workspace_sizes(P: int, W: int, H: int, cap: int):
+    key = (P, W, H, cap)
+    hit = _ws_cache.get(key)
+    if hit is not None:
+        return hit
     g, i, b = C.c_size_t(), C.c_size_t(), C.c_size_t()
     _lib.check(_lib.load().egs_workspace_sizes(P, W, H, cap, C.byref(g), C.byref(i), C.byref(b)), "workspace_sizes")
-    return g.value, i.value, b.value
+    if len(_ws_cache) > 256:
+        _ws_cache.clear()
+    _ws_cache[key] = (g.value, i.value, b.value)
+    return _ws_cache[key]
 
 
 class ForwardState:
