@@ -5,6 +5,7 @@
 // Replaces preprocessCUDA<3> (DGS/cuda_rasterizer/forward.cu:158-301), computeCov2DCUDA + preprocessCUDA<3> (bwd)
 // (DGS/cuda_rasterizer/backward.cu:144-416) and checkFrustum (DGS/cuda_rasterizer/rasterizer_impl.cu:54-66).
 #include "egs_surfel_math.cuh"
+#include <stdlib.h>
 
 #define SURF_THREADS 128
 #define SH_PITCH 49   // floats per staged SH row (48 + 1: conflict-free 4-byte accesses, one row per thread)
@@ -26,23 +27,42 @@ __device__ __forceinline__ void unstage_sh_rows(const float* s_sh, float* __rest
     }
 }
 
-// SH_SMEM: the CTA's SH block (M == 16: 128 x 192 B, contiguous) is staged through shared memory with fully
+#define SH_BULK_PITCH 52   // floats per row for the bulk-copied layout: 208-B rows keep 16-B alignment and make the
+                           // per-thread LDS.128 of a quarter-warp conflict-free (52 mod 32 = 20 -> 8 distinct 4-bank groups)
+
+// SH_SMEM = 1: the CTA's SH block (M == 16: 128 x 192 B, contiguous) is staged through shared memory with fully
 // coalesced 16-byte loads and read on demand, instead of living in 48 registers per thread.
-template <bool SH_SMEM>
+// SH_SMEM = 2: every thread issues ONE 192-byte bulk copy (cp.async.bulk -> mbarrier, the TMA engine) of its SH row at
+// kernel start and waits for it only after the projection / culling math, so the fetch overlaps ~1000 instructions
+// of arithmetic and costs one instruction instead of 12 LDG + 48 STS.
+template <int SH_SMEM>
 __global__ void __launch_bounds__(SURF_THREADS)
 k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
                  const float* __restrict__ colors, const int32_t* __restrict__ tile_mask, GeomView g, ImgView im,
                  int32_t* __restrict__ radii, uint8_t* __restrict__ active) {
     __shared__ FrameConst fc;
-    __shared__ float s_sh[SH_SMEM ? SURF_THREADS * SH_PITCH : 1];
+    __shared__ __align__(128) float s_sh[SH_SMEM == 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
+    __shared__ __align__(8) unsigned long long s_bar;
     load_frame_const(fc, f);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (SH_SMEM) {
+    const uint32_t bar = smem_addr(&s_bar);
+    if (SH_SMEM == 1) {
         const int row0 = blockIdx.x * SURF_THREADS;
         stage_sh_rows(s_sh, shs + (size_t)48 * row0, min(SURF_THREADS, f.num_surfels - row0));
     }
+    if (SH_SMEM == 2 && threadIdx.x == 0) {
+        mbar_init(bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (SH_SMEM == 2) {
+        const int row0 = blockIdx.x * SURF_THREADS;
+        const int rows = min(SURF_THREADS, f.num_surfels - row0);
+        if (threadIdx.x == 0) mbar_expect_tx(bar, 192u * (uint32_t)rows);
+        if ((int)threadIdx.x < rows)
+            bulk_copy_g2s(smem_addr(s_sh) + 4u * SH_BULK_PITCH * threadIdx.x, shs + (size_t)48 * (row0 + threadIdx.x), 192u, bar);
+    }
     const bool valid = i < f.num_surfels;
     bool visible = false;
     if (valid) {
@@ -55,7 +75,10 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
         uint32_t cnt = 0;
         if (o.radius > 0) {
             visible = true;
-            if (SH_SMEM) {
+            if (SH_SMEM == 2) {
+                mbar_wait(bar, 0u);
+                surfel_color(fc, mean, s_sh + threadIdx.x * SH_BULK_PITCH, true, o);
+            } else if (SH_SMEM == 1) {
                 surfel_color(fc, mean, s_sh + threadIdx.x * SH_PITCH, true, o);
             } else if (use_sh) {
                 // generic layout: this surfel's 3*(D+1)^2 floats into registers (16-byte vectors when rows allow it)
@@ -100,10 +123,13 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, visible);
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&im.counters->num_visible, __popc(ballot));
+    if (SH_SMEM == 2) mbar_wait(bar, 0u);   // the CTA must not retire while bulk copies into its shared memory are in flight
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <bool SH_SMEM>
+// SH_SMEM = 2: the SH row of every VISIBLE surfel arrives by one 192-byte bulk copy issued at kernel start (culled
+// rows are not fetched at all) and dL/dSH leaves by one bulk store per row; no CTA barrier around either.
+template <int SH_SMEM>
 __global__ void __launch_bounds__(SURF_THREADS)
 k_surfel_backward(const egs_frame f, int first, int count, const float* __restrict__ means,
                   const float* __restrict__ shs, const float* __restrict__ colors, const float* __restrict__ scales,
@@ -112,23 +138,40 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
                   float* __restrict__ d_sh, float* __restrict__ d_scales, float* __restrict__ d_rots,
                   float* __restrict__ d_means2D, float* __restrict__ d_colors, float* __restrict__ d_cov3D) {
     __shared__ FrameConst fc;
-    __shared__ float s_sh[SH_SMEM ? SURF_THREADS * SH_PITCH : 1];
+    __shared__ __align__(128) float s_sh[SH_SMEM == 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
+    __shared__ __align__(8) unsigned long long s_bar;
+    constexpr int PITCH = SH_SMEM == 2 ? SH_BULK_PITCH : SH_PITCH;
     load_frame_const(fc, f);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int row0 = first + blockIdx.x * SURF_THREADS;
     const int rows = min(SURF_THREADS, first + count - row0);
-    if (SH_SMEM) stage_sh_rows(s_sh, shs + (size_t)48 * row0, rows);
+    const uint32_t bar = smem_addr(&s_bar);
+    if (SH_SMEM == 1) stage_sh_rows(s_sh, shs + (size_t)48 * row0, rows);
+    if (SH_SMEM == 2 && threadIdx.x == 0) {
+        mbar_init(bar, SURF_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const bool valid = k < count;
     const int i = first + k;
     const int M = fc.M;
     const bool use_sh = colors == nullptr;
+    const uint32_t row_smem = smem_addr(s_sh) + 4u * PITCH * threadIdx.x;
+    if (SH_SMEM == 2) {
+        // every thread arrives once; the threads of visible surfels add their row's bytes and start the copy
+        if (valid && radii[i] > 0) {
+            mbar_expect_tx(bar, 192u);
+            bulk_copy_g2s(row_smem, shs + (size_t)48 * i, 192u, bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    }
     if (valid) {
         float g16[16];
         SurfelBwd o;
         const bool vis = radii[i] > 0;
         float* my_sh = use_sh ? d_sh + (size_t)3 * M * i : nullptr;
-        float* row = s_sh + threadIdx.x * SH_PITCH;
+        float* row = s_sh + threadIdx.x * PITCH;
         if (vis) {
             const float4* grow = reinterpret_cast<const float4*>(sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i);
 #pragma unroll
@@ -143,6 +186,7 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
                 const float gcol[3] = {g16[6], g16[7], g16[8]};
                 float add[3];
                 if (SH_SMEM) {
+                    if (SH_SMEM == 2) mbar_wait(bar, 0u);
                     // in place: sh_backward finishes reading the row before its first store
                     sh_backward(fc.D, row, dir, (uint32_t)g.clamped[i], gcol,
                                 [row](int kk, int ch, float v) { row[3 * kk + ch] = v; }, add);
@@ -215,9 +259,17 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
             for (int q = 0; q < 6; q++) d_cov3D[6 * (size_t)i + q] = o.d_cov3D[q];
         }
     }
-    if (SH_SMEM) {
+    if (SH_SMEM == 1) {
         __syncthreads();
         unstage_sh_rows(s_sh, d_sh + (size_t)48 * row0, rows); // coalesced 16-byte stores of the CTA's dL/dSH block
+    }
+    if (SH_SMEM == 2) {
+        mbar_wait(bar, 0u);   // no copy into this CTA's shared memory may be in flight when it retires
+        if (valid) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic-proxy row writes -> async proxy
+            bulk_copy_s2g(d_sh + (size_t)48 * i, row_smem, 192u);
+        }
+        bulk_commit_wait_read();   // the row must stay in shared memory until the store has read it
     }
 }
 
@@ -248,11 +300,21 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
     if (P == 0) return cudaSuccess;
     // staged-SH fast path: SH colours with exactly 16 coefficients per surfel and 16-byte aligned rows
     const bool sh_smem = colors == nullptr && f.sh_coeffs == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0;
-    if (sh_smem)
-        k_surfel_forward<true><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
-                                                               radii, active);
+    // EGS_SH_STAGE: "ldg" = LDG + STS staging, "bulk" = TMA bulk copies; default = bulk here (measured at C3:
+    // 96 -> 87 us, the fetch overlaps the projection math), ldg in the backward (bulk measured equal: 114 vs 115 us)
+    static int sh_bulk = -1;
+    if (sh_bulk < 0) {
+        const char* e = getenv("EGS_SH_STAGE");
+        sh_bulk = (e && e[0] == 'l') ? 0 : 1;
+    }
+    if (sh_smem && sh_bulk)
+        k_surfel_forward<2><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
+                                                            radii, active);
+    else if (sh_smem)
+        k_surfel_forward<1><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
+                                                            radii, active);
     else
-        k_surfel_forward<false><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
+        k_surfel_forward<0><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
                                                                 im, radii, active);
     return cudaGetLastError();
 }
@@ -265,12 +327,21 @@ cudaError_t launch_surfel_backward(const egs_frame& f, int first, int count, con
     if (count <= 0) return cudaSuccess;
     const bool sh_smem = colors == nullptr && f.sh_coeffs == 16 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(d_sh) & 15) == 0;
-    if (sh_smem)
-        k_surfel_backward<true><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
+    static int sh_bulk = -1;
+    if (sh_bulk < 0) {
+        const char* e = getenv("EGS_SH_STAGE");
+        sh_bulk = (e && e[0] == 'b') ? 1 : 0;
+    }
+    if (sh_smem && sh_bulk)
+        k_surfel_backward<2><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
+                                                                 radii, g, sg, d_means, d_opacity, d_sh, d_scales,
+                                                                 d_rots, d_means2D, d_colors, d_cov3D);
+    else if (sh_smem)
+        k_surfel_backward<1><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
                                                                     radii, g, sg, d_means, d_opacity, d_sh, d_scales,
                                                                     d_rots, d_means2D, d_colors, d_cov3D);
     else
-        k_surfel_backward<false><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
+        k_surfel_backward<0><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
                                                                      radii, g, sg, d_means, d_opacity, d_sh, d_scales,
                                                                      d_rots, d_means2D, d_colors, d_cov3D);
     return cudaGetLastError();

@@ -369,10 +369,11 @@ def test_backward_kernel_variants_agree():
     assert rel_err(outs["warp"], sg) <= TOL
 
 
-def test_forward_tma_variant_is_bit_identical():
-    """EGS_FWD_KERNEL=bulk (records staged by cp.async.bulk / mbarrier, double-buffered) performs the same arithmetic
-    in the same order as the default forward: images, saved state and the screen gradients that the backward derives
-    from its hit lists must be identical."""
+def test_tma_staged_variants_are_bit_identical():
+    """The TMA (cp.async.bulk + mbarrier) staging variants perform the same arithmetic in the same order as the LDG + STS
+    ones: EGS_FWD_KERNEL=bulk (record batches of the compositing forward, double-buffered) and EGS_SH_STAGE=bulk / ldg
+    (SH rows of the per-surfel kernels; the default mixes them).  Images, saved state and per-surfel gradients must be
+    identical; the screen gradients (float atomics) agree to their run-to-run spread."""
     import subprocess
     import sys
     code = (
@@ -380,18 +381,25 @@ def test_forward_tma_variant_is_bit_identical():
         "import test_parity_gpu as T\n"
         "o = T.cuda_run(sys.argv[2])\n"
         "np.savez(sys.argv[1], color=o['color'], depth=o['depth'], normal=o['normal_img'], opacity=o['opacity'],\n"
-        "         n_contrib=o['n_contrib'], final_T=o['final_T'], g=o['g_screen'])\n"
+        "         n_contrib=o['n_contrib'], final_T=o['final_T'], radii=o['radii'], g=o['g_screen'],\n"
+        "         g_sh=o['g_sh'], g_means=o['g_means3D'])\n"
     ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
+    variants = {"base": {"EGS_FWD_KERNEL": "ldg", "EGS_SH_STAGE": "ldg"}, "fwd_bulk": {"EGS_FWD_KERNEL": "bulk", "EGS_SH_STAGE": "ldg"},
+                "sh_bulk": {"EGS_FWD_KERNEL": "ldg", "EGS_SH_STAGE": "bulk"}, "default": {}}
     for case in ("c1_posed_bg", "small_deg0_ragged"):
         outs = {}
-        for variant in ("ldg", "bulk"):
-            path = "/tmp/egs_fwd_%s.npz" % variant
-            env = dict(os.environ, EGS_FWD_KERNEL=variant)
+        for name, extra in variants.items():
+            path = "/tmp/egs_var_%s.npz" % name
+            env = {k: v for k, v in os.environ.items() if k not in ("EGS_FWD_KERNEL", "EGS_SH_STAGE")}
+            env.update(extra)
             subprocess.run([sys.executable, "-c", code, path, case], check=True, env=env, cwd=util.ROOT)
-            outs[variant] = np.load(path)
-        for k in ("color", "depth", "normal", "opacity", "n_contrib", "final_T"):
-            assert np.array_equal(outs["ldg"][k], outs["bulk"][k]), (case, k)
-        assert rel_err(outs["bulk"]["g"], outs["ldg"]["g"]) <= 2e-6, case      # float atomics: order differs run to run
+            outs[name] = np.load(path)
+        for name in ("fwd_bulk", "sh_bulk", "default"):
+            for k in ("color", "depth", "normal", "opacity", "n_contrib", "final_T", "radii"):
+                assert np.array_equal(outs["base"][k], outs[name][k], equal_nan=True), (case, name, k)
+            assert rel_err(outs[name]["g"], outs["base"]["g"]) <= 2e-6, (case, name)
+            assert rel_err(outs[name]["g_sh"], outs["base"]["g_sh"]) <= 2e-6, (case, name)
+            assert rel_err(outs[name]["g_means"], outs["base"]["g_means"]) <= 2e-6, (case, name)
 
 
 def _random_case(seed, P, W, H, deg, layers=3, big=False, dense_tile=False):
