@@ -13,6 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 
 EGS_FWD_REUSE_BINNING = 1
+EGS_FWD_NO_SAVE = 2
 EGS_BWD_GRADS_PREZEROED = 1
 SCREEN_GRAD_STRIDE = 16
 
@@ -38,6 +39,7 @@ SIGNATURES = {
     "egs_error_string": (C.c_char_p, [C.c_int]),
     "egs_workspace_sizes": (C.c_int, [_I32, _I32, _I32, _I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                       C.POINTER(C.c_size_t)]),
+    "egs_bin_bytes_forward_only": (C.c_int, [_I64, C.POINTER(C.c_size_t)]),
     "egs_forward_plan": (C.c_int, [C.POINTER(Frame)] + [_P] * 13),
     "egs_forward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),
     "egs_backward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),

@@ -12,7 +12,7 @@ cudaError_t launch_tile_scan(ImgView, int, long long, cudaStream_t);
 cudaError_t launch_emit_sort(int, int, int, const int32_t*, GeomView, const int32_t*, ImgView, BinView, long long,
                              cudaStream_t);
 cudaError_t launch_render_forward(const egs_frame&, GeomView, ImgView, BinView, long long, float*, float*, float*,
-                                  float*, cudaStream_t);
+                                  float*, bool, cudaStream_t);
 cudaError_t launch_render_backward(const egs_frame&, GeomView, ImgView, BinView, long long, const float*, const float*,
                                    const float*, const float*, float*, cudaStream_t);
 
@@ -73,6 +73,12 @@ EGS_API int egs_workspace_sizes(int32_t P, int32_t width, int32_t height, int64_
     return 0;
 }
 
+EGS_API int egs_bin_bytes_forward_only(int64_t cap_instances, size_t* bin_bytes) {
+    if (cap_instances < 0 || !bin_bytes) return EGS_E_BADARG;
+    *bin_bytes = bin_bytes_forward_only((size_t)cap_instances);
+    return 0;
+}
+
 EGS_API int egs_forward_plan(const egs_frame* f, const float* means3D, const float* shs, const float* colors_precomp,
                      const float* opacities, const float* scales, const float* rotations, const int32_t* tile_mask,
                      void* geom, void* img, int32_t* radii, uint8_t* active_mask, egs_counters* counters_host,
@@ -118,7 +124,7 @@ EGS_API int egs_forward_render(const egs_frame* f, const int32_t* tile_mask, con
     if (!(flags & EGS_FWD_REUSE_BINNING))
         EGS_TRY(launch_emit_sort(P, gx, gy, radii, g, tile_mask, im, bn, (long long)cap_instances, s));
     EGS_TRY(launch_render_forward(*f, g, im, bn, (long long)cap_instances, out_color, out_normal, out_depth,
-                                  out_opacity, s));
+                                  out_opacity, (flags & EGS_FWD_NO_SAVE) == 0, s));
     if (counters_host) EGS_TRY(cudaMemcpyAsync(counters_host, im.counters, sizeof(egs_counters), cudaMemcpyDeviceToHost, s));
     return 0;
 }

@@ -149,6 +149,10 @@ EGS_HD BinView carve_bin(void* base, size_t cap) {
     v.bytes = o + 256;
     return v;
 }
+// size of the prefix a forward-only render touches (keys + point list)
+EGS_HD size_t bin_bytes_forward_only(size_t cap) {
+    return egs_align_up(egs_align_up(8 * cap, 256) + 4 * cap, 256) + 256;
+}
 
 // getRect of the reference (auxiliary.h:47-57): float arithmetic, truncation toward zero, clamped to the grid.
 EGS_HD void egs_tile_rect(float px, float py, int radius, int gx, int gy, int& x0, int& y0, int& x1, int& y1) {

@@ -39,14 +39,17 @@ __device__ __forceinline__ uint32_t block_mask_f(float x, float y, uint32_t ext,
     return m;
 }
 
-template <bool HITLIST>
+// MODE 0: blend masks as 8 words per instance (tile-wide backward variants); 1: per-block hit lists (default);
+// 2: forward-only render (EGS_FWD_NO_SAVE): nothing is saved for a backward.
+template <int MODE>
 __global__ void __launch_bounds__(EGS_TILE_THREADS, 6)
 k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const SplatRecord* __restrict__ rec, ImgView im,
                  BinView bn, long long cap, float* __restrict__ out_color, float* __restrict__ out_normal,
                  float* __restrict__ out_depth, float* __restrict__ out_opac) {
     __shared__ float4 s_rec[FWD_BATCH * 4];
     __shared__ uint32_t s_wm[FWD_BATCH];
-    __shared__ __align__(16) uint32_t s_lm[FWD_BATCH * 8];   // blend masks of the batch: [instance][block], HITLIST: [block][instance]
+    constexpr bool HITLIST = MODE == 1, SAVE = MODE != 2;
+    __shared__ __align__(16) uint32_t s_lm[SAVE ? FWD_BATCH * 8 : 4];   // blend masks of the batch: [instance][block], HITLIST: [block][instance]
 
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
@@ -67,9 +70,11 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
             for (int ch = 0; ch < 3; ch++) { out_color[ch * HW + pix] = 0.f; out_normal[ch * HW + pix] = 0.f; }
             out_depth[pix] = 0.f;
             out_opac[pix] = 0.f;
-            im.final_T[pix] = 0.f;   // saved state of never-composited tiles reads as zero (deterministic workspace)
-            im.final_D[pix] = 0.f;
-            im.n_contrib[pix] = 0u;
+            if (SAVE) {
+                im.final_T[pix] = 0.f;   // saved state of never-composited tiles reads as zero (deterministic workspace)
+                im.final_D[pix] = 0.f;
+                im.n_contrib[pix] = 0u;
+            }
         }
         if (HITLIST && threadIdx.x < 8) im.hit_count[8 * tile + threadIdx.x] = 0u;
         return;
@@ -105,8 +110,10 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
             s_rec[threadIdx.x * 4 + 2] = c; s_rec[threadIdx.x * 4 + 3] = d;
         }
         s_wm[threadIdx.x] = wm;
-        reinterpret_cast<uint4*>(s_lm)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
-        reinterpret_cast<uint4*>(s_lm)[threadIdx.x + FWD_BATCH] = make_uint4(0u, 0u, 0u, 0u);
+        if (SAVE) {
+            reinterpret_cast<uint4*>(s_lm)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4*>(s_lm)[threadIdx.x + FWD_BATCH] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         if (!__all_sync(0xffffffffu, done)) {
             const int chunks = (m + 31) >> 5;
@@ -124,9 +131,11 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                     const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
                     bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                     if (ok && test_T < 0.0001f) { done = true; ok = false; }   // stops WITHOUT blending this one
-                    const unsigned bm = __ballot_sync(0xffffffffu, ok);
-                    if (bm == 0u) continue;
-                    sts32(lm_warp + LM_STRIDE * (uint32_t)j, bm);   // every lane stores the same word: one wavefront
+                    if (SAVE) {
+                        const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                        if (bm == 0u) continue;
+                        sts32(lm_warp + LM_STRIDE * (uint32_t)j, bm);   // every lane stores the same word: one wavefront
+                    }
                     if (ok) {
                         const float w = __fmul_rn(alpha, T);
                         const float4 q2 = lds128(ra + 32u), q3 = lds128(ra + 48u);
@@ -154,7 +163,7 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
                 }
             }
         }
-        if (!HITLIST) {
+        if (MODE == 0) {
             __syncthreads();
             // publish the blend masks of this batch: 32 contiguous bytes per instance
             if ((int)threadIdx.x < m) {
@@ -167,9 +176,11 @@ k_render_forward(int W, int H, int gx, const float* __restrict__ bg, const Splat
     if (HITLIST && lane == 0) im.hit_count[8 * tile + warp] = hcnt;
     if (inside) {
         T = fminf(0.999999f, T);
-        im.final_T[pix] = T;
-        im.final_D[pix] = D;
-        im.n_contrib[pix] = last;
+        if (SAVE) {
+            im.final_T[pix] = T;
+            im.final_D[pix] = D;
+            im.n_contrib[pix] = last;
+        }
         out_color[pix] = fmaf(T, __ldg(bg), C0);
         out_color[HW + pix] = fmaf(T, __ldg(bg + 1), C1);
         out_color[2 * HW + pix] = fmaf(T, __ldg(bg + 2), C2);
@@ -351,7 +362,7 @@ k_render_forward_bulk(int W, int H, int gx, const float* __restrict__ bg, const 
 }
 
 cudaError_t launch_render_forward(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
-                                  float* out_color, float* out_normal, float* out_depth, float* out_opac,
+                                  float* out_color, float* out_normal, float* out_depth, float* out_opac, bool save,
                                   cudaStream_t s) {
     const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
     static int fwd_bulk = -1;
@@ -359,14 +370,17 @@ cudaError_t launch_render_forward(const egs_frame& f, GeomView g, ImgView im, Bi
         const char* e = getenv("EGS_FWD_KERNEL");
         fwd_bulk = (e && e[0] == 'b') ? 1 : 0;
     }
-    if (egs_bwd_variant() == 3 && fwd_bulk)
+    if (!save)
+        k_render_forward<2><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, out_color,
+                                                                 out_normal, out_depth, out_opac);
+    else if (egs_bwd_variant() == 3 && fwd_bulk)
         k_render_forward_bulk<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
                                                                    out_color, out_normal, out_depth, out_opac);
     else if (egs_bwd_variant() == 3)
-        k_render_forward<true><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
+        k_render_forward<1><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
                                                                     out_color, out_normal, out_depth, out_opac);
     else
-        k_render_forward<false><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
+        k_render_forward<0><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap,
                                                                      out_color, out_normal, out_depth, out_opac);
     return cudaGetLastError();
 }

@@ -53,7 +53,7 @@ class SplatContext:
 
     # each stage is one C-ABI call; `mark(stage_name)` (optional) is invoked after each for event timing
     def forward(self, means3D, shs, colors_precomp, opacities, scales, rotations, tile_mask=None,
-                mark: Optional[Callable[[str], None]] = None, fetch_counters: bool = False) -> None:
+                mark: Optional[Callable[[str], None]] = None, fetch_counters: bool = False, save: bool = True) -> None:
         lib, fr = self.lib, self.frame
         stream = R._stream_ptr(self.device)
         tm = None if tile_mask is None else tile_mask.data_ptr()
@@ -66,7 +66,8 @@ class SplatContext:
         _lib.check(lib.egs_forward_render(C.byref(fr), tm, self.radii.data_ptr(), self.geom.data_ptr(),
                                           self.img.data_ptr(), self.bin.data_ptr(), self.cap, self.color.data_ptr(),
                                           self.normal.data_ptr(), self.depth.data_ptr(), self.opacity.data_ptr(),
-                                          self.counters_host.data_ptr() if fetch_counters else None, 0, stream),
+                                          self.counters_host.data_ptr() if fetch_counters else None,
+                                          0 if save else _lib.EGS_FWD_NO_SAVE, stream),
                    "forward_render")
         if mark:
             mark("render")

@@ -152,11 +152,20 @@ def workspace_sizes(P: int, W: int, H: int, cap: int):
 class ForwardState:
     """Everything a forward leaves behind for the backward (the reference's geomBuffer / binningBuffer /
     imgBuffer / tile_indices / radii saved set, __init__.py:97-100)."""
-    __slots__ = ("frame", "keep", "geom", "img", "bin", "cap", "radii", "num_rendered", "tile_num", "tile_mask")
+    __slots__ = ("frame", "keep", "geom", "img", "bin", "cap", "radii", "num_rendered", "tile_num", "tile_mask", "saved")
 
 
-def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotations, tile_mask, capacity=None):
-    """Run the CUDA forward.  Returns (color, normal, depth, opacity, active_mask, radii, ForwardState)."""
+def _bin_bytes_forward_only(cap: int) -> int:
+    b = C.c_size_t()
+    _lib.check(_lib.load().egs_bin_bytes_forward_only(cap, C.byref(b)), "bin_bytes_forward_only")
+    return b.value
+
+
+def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotations, tile_mask, capacity=None,
+                save=True):
+    """Run the CUDA forward.  Returns (color, normal, depth, opacity, active_mask, radii, ForwardState).
+    save=False: forward-only render (EGS_FWD_NO_SAVE): nothing is kept for a backward, the binning workspace is 12
+    instead of 76 bytes per instance."""
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:60-62
@@ -193,7 +202,7 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
         active = torch.empty((P,), dtype=torch.bool, device=device)
 
         st = ForwardState()
-        st.frame, st.keep, st.radii, st.tile_mask = frame, keep, radii, tile_mask
+        st.frame, st.keep, st.radii, st.tile_mask, st.saved = frame, keep, radii, tile_mask, bool(save)
         gb, ib, _ = workspace_sizes(P, W, H, 0)
         st.geom = torch.empty((gb,), **u8)
         st.img = torch.empty((ib,), **u8)
@@ -221,12 +230,13 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
         else:
             st.cap = int(capacity)
             st.num_rendered = st.tile_num = -1  # unknown on the host by design
-        _, _, bb = workspace_sizes(P, W, H, st.cap)
+        bb = workspace_sizes(P, W, H, st.cap)[2] if save else _bin_bytes_forward_only(st.cap)
         st.bin = torch.empty((bb,), **u8)
         _lib.check(lib.egs_forward_render(C.byref(frame), _ptr(tile_mask), _ptr(radii), st.geom.data_ptr(),
                                           st.img.data_ptr(), st.bin.data_ptr(), st.cap, color.data_ptr(),
                                           normal.data_ptr(), depth.data_ptr(), opac.data_ptr(),
-                                          None if exact else host.data_ptr(), 0, stream), "forward_render")
+                                          None if exact else host.data_ptr(), 0 if save else _lib.EGS_FWD_NO_SAVE,
+                                          stream), "forward_render")
         if not exact:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
@@ -241,6 +251,8 @@ def backward_raw(st: ForwardState, means3D, shs, colors_precomp, scales, rotatio
     device = means3D.device
     P = means3D.size(0)
     frame = st.frame
+    if not getattr(st, "saved", True):
+        raise RuntimeError("eggsplat: this forward was a forward-only render (save=False / no_grad): no backward state")
     with torch.cuda.device(device):
         stream = _stream_ptr(device)
         f32 = dict(dtype=torch.float32, device=device)
@@ -341,6 +353,13 @@ class _RasterizeGaussians(torch.autograd.Function):
 
 def rasterize_gaussians(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, tile_mask,
                         raster_settings):
+    needs_grad = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in (means3D, sh, colors_precomp, opacities, scales, rotations))
+    if not needs_grad and not raster_settings.debug and not _present(cov3Ds_precomp):
+        # the reference under torch.no_grad() (model maps for tracking / fusion, mapper.py:227,497): forward-only render
+        color, normal, depth, opac, active_mask, radii, _st = forward_raw(
+            raster_settings, means3D, sh, colors_precomp, opacities, scales, rotations, tile_mask, save=False)
+        return color, normal, depth, opac, active_mask, radii
     return _RasterizeGaussians.apply(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                      tile_mask, raster_settings)
 

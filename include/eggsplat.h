@@ -54,6 +54,9 @@ extern "C" {
 
 /* flags of egs_forward_render */
 #define EGS_FWD_REUSE_BINNING 1 /* skip emission + sort: composite again from the lists already in `bin` */
+#define EGS_FWD_NO_SAVE 2       /* forward-only render (the reference under torch.no_grad(), e.g. the model maps of
+                                   tracking / fusion, mapper.py:227,497): nothing is kept for a backward -- no per-block hit
+                                   lists, no saved per-pixel state -- and `bin` needs only egs_bin_bytes_forward_only() */
 /* flags of egs_backward_render */
 #define EGS_BWD_GRADS_PREZEROED 1 /* caller already zeroed (or pre-loaded) screen_grads: accumulate on top */
 
@@ -88,6 +91,10 @@ EGS_API const char* egs_error_string(int code);
  * binning workspace is sized for; pass the exact count read back after egs_forward_plan, or an upper bound. */
 EGS_API int egs_workspace_sizes(int32_t num_surfels, int32_t width, int32_t height, int64_t cap_instances,
                         size_t* geom_bytes, size_t* img_bytes, size_t* bin_bytes);
+
+/* Bytes of the binning workspace when egs_forward_render is called with EGS_FWD_NO_SAVE (12 instead of 76 bytes per
+ * instance: sort keys + point list only). */
+EGS_API int egs_bin_bytes_forward_only(int64_t cap_instances, size_t* bin_bytes);
 
 /*
  * Per-surfel projection.  Writes radii[P] (0 = culled), active_mask[P] (1 = inside the frustum), the packed

@@ -369,6 +369,32 @@ def test_backward_kernel_variants_agree():
     assert rel_err(outs["warp"], sg) <= TOL
 
 
+def test_forward_only_render_matches_and_keeps_no_state():
+    """Under torch.no_grad() (or with inputs that need no gradient) the drop-in takes the forward-only path
+    (EGS_FWD_NO_SAVE): same images bit for bit, a 6x smaller binning workspace, and no backward state."""
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R
+    cam, sc, g, bg, mask, deg = util.case_inputs("c1_posed_bg")
+    s = _settings(E, cam, bg, deg)
+    leaf = {k: _t(sc[k]).requires_grad_(True) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
+    call = lambda: E.GaussianRasterizer(s)(means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"],
+                                           scales=leaf["scales"], rotations=leaf["rotations"], tile_mask=_t(mask))
+    with_grad = call()
+    with torch.no_grad():
+        no_grad = call()
+    assert with_grad[0].grad_fn is not None and no_grad[0].grad_fn is None and not no_grad[0].requires_grad
+    for a, b in zip(with_grad, no_grad):
+        assert torch.equal(a, b)
+    empty = torch.Tensor([])
+    args = (s, leaf["xyz"].detach(), leaf["shs"].detach(), empty, leaf["opacity"].detach(), leaf["scales"].detach(),
+            leaf["rotations"].detach(), _t(mask))
+    st_full, st_fwd = R.forward_raw(*args)[6], R.forward_raw(*args, save=False)[6]
+    assert st_fwd.bin.numel() * 5 < st_full.bin.numel()
+    with pytest.raises(RuntimeError, match="forward-only"):
+        R.backward_raw(st_fwd, args[1], args[2], empty, args[5], args[6], _t(g["color"]), _t(g["normal"]),
+                       _t(g["depth"]), _t(g["opacity"]))
+
+
 def test_tma_staged_variants_are_bit_identical():
     """The TMA (cp.async.bulk + mbarrier) staging variants perform the same arithmetic in the same order as the LDG + STS
     ones: EGS_FWD_KERNEL=bulk (record batches of the compositing forward, double-buffered) and EGS_SH_STAGE=bulk / ldg
