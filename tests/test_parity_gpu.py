@@ -329,6 +329,40 @@ def test_properties_at_full_size():
     assert bool((nz[1:, 0] == nz[:-1, 1]).all()) and int(nz[0, 0]) == 0 and int(nz[-1, 1]) == I
     assert int((dbg["tile_indices"] >= 0).sum()) == st.tile_num == int((lens > 0).sum())
     assert bool(torch.isfinite(color).all()) and bool(torch.isfinite(depth).all())
+    # per-block hit lists (what the backward walks): bounded by the tile list, valid ids, non-empty masks, depth order
+    # preserved, and the union of a block's masks is exactly the set of its pixels that blended anything
+    W, H = cam.width, cam.height
+    T = ranges.shape[0]
+    al = lambda v: (v + 255) // 256 * 256
+    cap = st.cap
+    hits = st.bin[al(al(8 * cap) + 4 * cap):][: 64 * cap].view(torch.int32).view(-1, 2)
+    o = 256 + al(4 * T) + al(4 * (T + 1)) + al(4 * T) + al(4 * T)
+    hit_count = st.img[o: o + 32 * T].view(torch.int32).long().view(T, 8)
+    assert bool((hit_count <= lens[:, None]).all()) and int(hit_count.sum()) > I
+    seg0 = (8 * ranges[:, 0])[:, None] + torch.arange(8, device=DEV)[None, :] * lens[:, None]       # [T, 8] first entry
+    blk = torch.repeat_interleave(torch.arange(8 * T, device=DEV), hit_count.reshape(-1))
+    first_of_blk = torch.cumsum(hit_count.reshape(-1), 0) - hit_count.reshape(-1)
+    pos = seg0.reshape(-1)[blk] + (torch.arange(blk.numel(), device=DEV) - first_of_blk[blk])
+    ids, masks = hits[pos, 0].long(), hits[pos, 1].long() & 0xFFFFFFFF
+    assert bool((masks != 0).all()) and bool((ids >= 0).all()) and bool((ids < P).all()) and bool((radii[ids] > 0).all())
+    hkey = (rec_depth[ids] << 32) | ids
+    assert bool(((hkey[1:] > hkey[:-1]) | (blk[1:] != blk[:-1])).all())
+    union = torch.zeros(8 * T, dtype=torch.int64, device=DEV)
+    for bit in range(32):
+        union.scatter_reduce_(0, blk, (masks >> bit) & 1, reduce="amax")
+        hitpix = union.clone() if bit == 0 else hitpix | (union << bit)
+        union.zero_()
+    gx = (W + 15) // 16
+    t_idx = torch.arange(T, device=DEV)
+    ncon = dbg["n_contrib"].view(H, W)
+    for b in (0, 5):   # spot-check two of the eight blocks of every tile, all 32 lanes
+        bx, by = (t_idx % gx) * 16 + (b & 1) * 8, (t_idx // gx) * 16 + (b >> 1) * 4
+        for lane in range(32):
+            px, py = bx + (lane & 7), by + (lane >> 3)
+            ok = (px < W) & (py < H)
+            blended = ncon[py.clamp(max=H - 1), px.clamp(max=W - 1)] > 0
+            bitset = ((hitpix.view(T, 8)[:, b] >> lane) & 1) > 0
+            assert bool(((blended == bitset) | ~ok).all()), (b, lane)
     # linearity in the tile mask: two disjoint shards reproduce the frame and sum to its gradients
     ty, tx = cam.tiles
     acc = None
