@@ -13,16 +13,12 @@
 // value), k_gn_solve_update (one thread) combines the terms, solves the 6x6 system, evaluates the convergence test and
 // applies update_transform to the pose ON THE DEVICE; egt_track_pyramid enqueues the whole coarse-to-fine loop
 // (2 launches per step) without a host sync.  HBM-bound streaming: ~120 B per pixel.
-#include "egs_common.cuh"
-#include "../../include/eggtrack.h"
+#include "egt_gn_math.cuh"
 
 namespace {
 
 #define GN_CTA 128
 #define GN_SUMS 56   // icp: 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (count); rgb: the same
-
-// F.grid_sample(align_corners=True): [-1, 1] -> [0, size - 1]
-__device__ __forceinline__ float unnormalize(float g, int size) { return (g + 1.f) * 0.5f * (float)(size - 1); }
 
 // The 28 sums of one term: upper triangle of J J^T (21), J r (6), count (1) -- padded to 32.
 __device__ __forceinline__ void outer_terms(float (&v)[32], bool valid, const float (&J)[6], float r) {
@@ -63,9 +59,7 @@ k_gn_accumulate(egt_level lv, const float* __restrict__ transform, float sine_th
     if (threadIdx.x < 16) s_T[threadIdx.x] = transform[threadIdx.x];
     __syncthreads();
     const float* T = s_T;
-    const int W = lv.width, H = lv.height;
-    const long long n = (long long)W * H;
-    const float fx = lv.fx, fy = lv.fy, cx = lv.cx, cy = lv.cy;
+    const long long n = (long long)lv.width * lv.height;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc_icp = 0.f, acc_rgb = 0.f;   // lane l: running sum of value l of each term
 
@@ -75,89 +69,19 @@ k_gn_accumulate(egt_level lv, const float* __restrict__ transform, float sine_th
         if (p - lane >= n) break;   // warp-uniform: the whole warp is past the image
         const bool in_img = p < n;
         const long long pc = in_img ? p : 0;
-        const int y = (int)(pc / W), x = (int)(pc - (long long)y * W);
-        // ---- projective_transform (optimizer.py:131-180)
-        const float us = ((float)x - cx) / fx, vs = ((float)y - cy) / fy, ds = lv.model_disp[pc];
-        float ut = T[0] * us + T[1] * vs + T[2] + T[3] * ds;
-        float vt = T[4] * us + T[5] * vs + T[6] + T[7] * ds;
-        const float zt = T[8] * us + T[9] * vs + T[10] + T[11] * ds;
-        float dt = T[12] * us + T[13] * vs + T[14] + T[15] * ds;
-        ut = ut / zt; vt = vt / zt; dt = dt / zt;
-        const float gx = 2.f * (fx * ut + cx) / (float)(W - 1) - 1.f;
-        const float gy = 2.f * (fy * vt + cy) / (float)(H - 1) - 1.f;
-        // both terms need the warped pixel inside (the ICP bound 0.98 is the wider one; NaN coordinates fail it) and
-        // the model mask (mask_prev)
-        const bool base = in_img && gx > -0.98f && gx < 0.98f && gy > -0.98f && gy < 0.98f && lv.model_mask[pc] != 0;
-        if (!__any_sync(0xffffffffu, base)) continue;
-        const float ix = unnormalize(gx, W), iy = unnormalize(gy, H);
-        float v[32];
-
-        // ---- icp_optimization (optimizer.py:317-377)
-        {
-            bool valid = base && lv.frame_mask[pc] != 0;    // mask_curr at the SAME pixel, not warped (as the reference)
-            float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r = 0.f;
-            if (valid) {
-                const float* vp = lv.model_vertex + 3 * pc;
-                const float* np_ = lv.model_normal + 3 * pc;
-                const float v0 = vp[0], v1 = vp[1], v2 = vp[2], n0 = np_[0], n1 = np_[1], n2 = np_[2];
-                const float pv0 = T[0] * v0 + T[1] * v1 + T[2] * v2 + T[3];
-                const float pv1 = T[4] * v0 + T[5] * v1 + T[6] * v2 + T[7];
-                const float pv2 = T[8] * v0 + T[9] * v1 + T[10] * v2 + T[11];
-                const float pn0 = T[0] * n0 + T[1] * n1 + T[2] * n2;
-                const float pn1 = T[4] * n0 + T[5] * n1 + T[6] * n2;
-                const float pn2 = T[8] * n0 + T[9] * n1 + T[10] * n2;
-                // nearest, padding border, align_corners: clip then round half to even
-                const int sx = (int)nearbyintf(fminf(fmaxf(ix, 0.f), (float)(W - 1)));
-                const int sy = (int)nearbyintf(fminf(fmaxf(iy, 0.f), (float)(H - 1)));
-                const long long q = (long long)sy * W + sx;
-                const float* vc = lv.frame_vertex + 3 * q;
-                const float* nc = lv.frame_normal + 3 * q;
-                const float c0 = nc[0], c1 = nc[1], c2 = nc[2];
-                const float d0 = vc[0] - pv0, d1 = vc[1] - pv1, d2 = vc[2] - pv2;
-                const float x0 = c1 * pn2 - c2 * pn1, x1 = c2 * pn0 - c0 * pn2, x2 = c0 * pn1 - c1 * pn0;   // cross(ncurr, nprev)
-                const float dist = sqrtf(d0 * d0 + d1 * d1 + d2 * d2), sine = sqrtf(x0 * x0 + x1 * x1 + x2 * x2);
-                const bool nan_ok = x0 == x0 && x1 == x1 && x2 == x2;
-                valid = nan_ok && pv2 > 0.f && sine < sine_thres && dist < dist_thres;
-                r = c0 * d0 + c1 * d1 + c2 * d2;
-                J[0] = c0; J[1] = c1; J[2] = c2;                                  // J = [ncurr, cross(vprev, ncurr)]
-                J[3] = pv1 * c2 - pv2 * c1; J[4] = pv2 * c0 - pv0 * c2; J[5] = pv0 * c1 - pv1 * c0;
-            }
+        GnWarp w;
+        egt_gn_warp(lv, T, pc, in_img, w);                     // projective_transform (optimizer.py:131-180)
+        if (!__any_sync(0xffffffffu, w.base)) continue;
+        float v[32], J[6], r;
+        {   // icp_optimization (optimizer.py:317-377)
+            const bool valid = egt_gn_icp_row(lv, T, pc, w, sine_thres, dist_thres, J, r);
             if (__any_sync(0xffffffffu, valid)) {
                 outer_terms(v, valid, J, r);
                 acc_icp += warp_transpose_sum32(v, lane);
             }
         }
-        // ---- rgb_optimization (optimizer.py:278-315)
-        if (use_rgb) {
-            bool valid = base && gx > -0.90f && gx < 0.90f && gy > -0.90f && gy < 0.90f && lv.frame_grad[3 * pc + 2] > 1.f;
-            float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, r = 0.f;
-            if (valid) {
-                // mask_curr: nearest, padding zeros
-                const int mx = (int)nearbyintf(ix), my = (int)nearbyintf(iy);
-                valid = mx >= 0 && mx < W && my >= 0 && my < H && lv.frame_mask[(long long)my * W + mx] != 0;
-            }
-            if (valid) {
-                // bilinear, padding zeros, align_corners
-                const float fx0 = floorf(ix), fy0 = floorf(iy);
-                const int x0 = (int)fx0, y0 = (int)fy0;
-                const float tx = ix - fx0, ty = iy - fy0;
-                const float w00 = (1.f - tx) * (1.f - ty), w10 = tx * (1.f - ty), w01 = (1.f - tx) * ty, w11 = tx * ty;
-                float sI = 0.f, sgx = 0.f, sgy = 0.f;
-                auto tap = [&](int xx, int yy, float w) {
-                    if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-                        const long long q = (long long)yy * W + xx;
-                        sI = fmaf(lv.frame_intensity[q], w, sI);
-                        sgx = fmaf(lv.frame_grad[3 * q], w, sgx);
-                        sgy = fmaf(lv.frame_grad[3 * q + 1], w, sgy);
-                    }
-                };
-                tap(x0, y0, w00); tap(x0 + 1, y0, w10); tap(x0, y0 + 1, w01); tap(x0 + 1, y0 + 1, w11);
-                r = lv.model_intensity[pc] - sI;
-                // J = Ji (1x2) @ Jc (2x6), Jc rows as in projective_transform
-                const float a = sgx * fx, b = sgy * fy;
-                J[0] = a * dt; J[1] = b * dt; J[2] = -(a * ut + b * vt) * dt;
-                J[3] = -a * ut * vt - b * (1.f + vt * vt); J[4] = a * (1.f + ut * ut) + b * ut * vt; J[5] = -a * vt + b * ut;
-            }
+        if (use_rgb) {   // rgb_optimization (optimizer.py:278-315)
+            const bool valid = egt_gn_rgb_row(lv, pc, w, J, r);
             if (__any_sync(0xffffffffu, valid)) {
                 outer_terms(v, valid, J, r);
                 acc_rgb += warp_transpose_sum32(v, lane);

@@ -3,6 +3,7 @@
 // arithmetic the kernels run against the oracle.  Never loaded by the product path.
 #include "../../eggfusion_b200/csrc/egs_surfel_math.cuh"
 #include "../../eggfusion_b200/csrc/egm_math.cuh"
+#include "../../eggfusion_b200/csrc/egt_gn_math.cuh"
 #include <cmath>
 #include <cstring>
 
@@ -120,6 +121,31 @@ void emu_adam_geom(int P, int step, const float* lrs /* xyz, opacity, scaling, r
         EgmRot rot;
         egm_normalize_quat(rotation_raw + 4 * i, rot);
         for (int k = 0; k < 4; k++) act_r[4 * i + k] = egm_nan_to_num(rot.qh[k]);
+    }
+}
+
+// ---- dense-tracker Gauss-Newton rows (egt_gn_math.cuh): the per-pixel sequence of k_gn_accumulate, sums in double ---
+void emu_gn_accumulate(const egt_level* lv, const float* T, float angle_thres_deg, float dist_thres, int use_rgb,
+                       double* sums /*[56]*/) {
+    for (int i = 0; i < 56; i++) sums[i] = 0.0;
+    const float sine_thres = (float)((double)angle_thres_deg * 3.14159265358979323846 / 180.0);
+    const long long n = (long long)lv->width * lv->height;
+    for (long long p = 0; p < n; p++) {
+        GnWarp w;
+        egt_gn_warp(*lv, T, p, true, w);
+        if (!w.base) continue;
+        float J[6], r;
+        for (int term = 0; term < (use_rgb ? 2 : 1); term++) {
+            const bool valid = term == 0 ? egt_gn_icp_row(*lv, T, p, w, sine_thres, dist_thres, J, r)
+                                         : egt_gn_rgb_row(*lv, p, w, J, r);
+            if (!valid) continue;
+            double* s = sums + 28 * term;
+            int k = 0;
+            for (int a = 0; a < 6; a++)
+                for (int b = a; b < 6; b++) s[k++] += (double)(J[a] * J[b]);
+            for (int a = 0; a < 6; a++) s[21 + a] += (double)(J[a] * r);
+            s[27] += 1.0;
+        }
     }
 }
 }

@@ -46,3 +46,38 @@ def test_gn_steps_reduce_the_icp_residual():
         cost.append(float(np.abs((ncurr * (vcurr - vprev)).sum(-1)).mean()))
         T = go.gn_step(model, frame, intr, T, mg.ANGLE_THRES, mg.DIST_THRES, True, 1e-4, 1e-6, 0.01, 0.001)["T_new"]
     assert cost[-1] < cost[0]
+
+
+def test_product_math_matches_oracle_on_cpu(hostemu):
+    """The product's per-pixel rows (eggfusion_b200/csrc/egt_gn_math.cuh, compiled for the CPU) against the oracle and
+    the reference goldens: same valid-pixel sets, J^T J / J^T r within 1e-4."""
+    import ctypes
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from eggfusion_b200._lib import Level
+    for name in mg.CASES:
+        model, frame, intr, T, dx = mg.case_inputs(name)
+        gold = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        H, W = model["mask"].shape[:2]
+        keep = [np.ascontiguousarray(model["disp"], np.float32), np.ascontiguousarray(model["vertex"], np.float32),
+                np.ascontiguousarray(model["normal"], np.float32), np.ascontiguousarray(model["mask"]).view(np.uint8),
+                np.ascontiguousarray(model["intensity"], np.float32), np.ascontiguousarray(frame["vertex"], np.float32),
+                np.ascontiguousarray(frame["normal"], np.float32), np.ascontiguousarray(frame["mask"]).view(np.uint8),
+                np.ascontiguousarray(frame["intensity"], np.float32), np.ascontiguousarray(frame["grad"], np.float32)]
+        lv = Level(W, H, float(intr[0]), float(intr[1]), float(intr[2]), float(intr[3]), *[a.ctypes.data for a in keep])
+        sums = np.zeros(56, np.float64)
+        Tc = np.ascontiguousarray(T, np.float32)
+        hostemu.emu_gn_accumulate(ctypes.byref(lv), Tc.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(mg.ANGLE_THRES),
+                                  ctypes.c_float(mg.DIST_THRES), ctypes.c_int(1), sums.ctypes.data_as(ctypes.c_void_p))
+
+        def tri(v):
+            M = np.zeros((6, 6))
+            k = 0
+            for r in range(6):
+                for c in range(r, 6):
+                    M[r, c] = M[c, r] = v[k]
+                    k += 1
+            return M
+        assert int(round(sums[27])) == int(gold["n_icp"]) and int(round(sums[55])) == int(gold["n_rgb"])
+        assert rel_err(tri(sums[:21]), gold["A_icp"]) <= 1e-4 and rel_err(sums[21:27], gold["b_icp"]) <= 1e-4
+        assert rel_err(tri(sums[28:49]), gold["A_rgb"]) <= 1e-4 and rel_err(sums[49:55], gold["b_rgb"]) <= 1e-4
