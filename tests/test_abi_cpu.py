@@ -110,6 +110,30 @@ def test_no_cpu_fallback():
           rotations=torch.zeros(4, 4))
 
 
+def test_mapping_and_tracking_mirrors_refuse_host_tensors():
+    """The N1 / N3 host mirrors (eggfusion_b200.mapping, .tracking) have no CPU path either."""
+    import types
+    from eggfusion_b200 import mapping as M, tracking as TR
+    w = M.MappingWeights()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.loss_seed(torch.zeros(3, 4, 4), torch.zeros(1, 4, 4), torch.zeros(3, 4, 4), torch.zeros(4, 4, 3), None, None,
+                    torch.ones(4, 4, dtype=torch.bool), None, w)
+    raw = {"xyz": torch.zeros(5, 3), "features_dc": torch.zeros(5, 1, 3), "features_rest": torch.zeros(5, 15, 3),
+           "scaling": torch.zeros(5, 3), "rotation": torch.ones(5, 4), "opacity": torch.zeros(5, 1)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.FrameBatchOptimizer(raw, M.LrParams(1e-5, 1e-3, 1e-5, 5e-4, 1e-4))
+    pyr = types.SimpleNamespace(**{k + "_pyramid": [torch.zeros(8, 8, c)] for k, c in
+                                   (("disp", 1), ("vertex", 3), ("normal", 3), ("mask", 1), ("intensity", 1), ("grad", 3))},
+                                intrinsic_pyramid=[torch.tensor([8.0, 8.0, 3.5, 3.5])])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        TR.make_level(pyr, pyr, 0)
+    # the ctypes structs mirror the C layouts (include/eggmap.h: egm_adam, include/eggtrack.h: egt_level)
+    import ctypes
+    from eggfusion_b200 import _lib
+    assert ctypes.sizeof(_lib.AdamHyper) == 3 * 8 + 6 * 4 + 4 + 2 * 4 + 4   # doubles first, padded to 8
+    assert ctypes.sizeof(_lib.Level) == 2 * 4 + 4 * 4 + 10 * 8
+
+
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under eggfusion_b200/ may reference it."""
     pkg = os.path.join(ROOT, "eggfusion_b200")
