@@ -260,11 +260,19 @@ cudaError_t launch_render_backward_gather(const egs_frame& f, GeomView g, ImgVie
 //   butterfly  16-shuffle transposing butterfly + shared-memory combine (this file)                      1.38 ms
 //   mma        cross-pixel sums on the tensor cores, mma.sync 3xTF32 (egs_render_bwd_mma.cu)             1.62 ms
 // The legacy mma.sync path costs more issue slots than it saves here.  All four are covered by the parity tests.
+//   lane       like warp, but the cross-pixel sums are taken by "a lane owns a splat" over 32-hit chunks with packed
+//              FP32 and broadcast weight reads (egs_render_bwd_lane.cu): default since round 2
+// Variants 3 (warp, lane) consume the forward's per-block hit lists, 0-2 its lane_masks.
+cudaError_t launch_render_backward_lane(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
+                                        const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
+                                        cudaStream_t s);
+static int g_bwd_lane = 1;
 int egs_bwd_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("EGS_BWD_KERNEL");
-        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : (e && e[0] == 'g') ? 2 : 3;   // default: warp
+        v = (e && e[0] == 'm') ? 1 : (e && e[0] == 'b') ? 0 : (e && e[0] == 'g') ? 2 : 3;   // default: lane
+        g_bwd_lane = (e && e[0] == 'w') ? 0 : 1;
     }
     return v;
 }
@@ -273,7 +281,9 @@ cudaError_t launch_render_backward(const egs_frame& f, GeomView g, ImgView im, B
                                    const float* gC, const float* gN, const float* gD, const float* gO, float* sg,
                                    cudaStream_t s) {
     if (egs_bwd_variant() == 1) return launch_render_backward_mma(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
-    if (egs_bwd_variant() == 3) return launch_render_backward_warp(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
+    if (egs_bwd_variant() == 3)
+        return g_bwd_lane ? launch_render_backward_lane(f, g, im, bn, cap, gC, gN, gD, gO, sg, s)
+                          : launch_render_backward_warp(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
     if (egs_bwd_variant() == 2) return launch_render_backward_gather(f, g, im, bn, cap, gC, gN, gD, gO, sg, s);
     const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
     k_render_backward<<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, gC, gN, gD,

@@ -366,15 +366,23 @@ k_render_forward_bulk(int W, int H, int gx, const float* __restrict__ bg, const 
     }
 }
 
+cudaError_t launch_render_forward2(const egs_frame&, GeomView, ImgView, BinView, long long, float*, float*, float*,
+                                   float*, bool, cudaStream_t);
+
+// EGS_FWD_KERNEL: unset / "pair" = two pixels per lane on the packed FP32 pipe (egs_render_fwd2.cu, default);
+// "ldg" = one pixel per lane (this file); "bulk" = one pixel per lane with TMA-staged batches (this file).
 cudaError_t launch_render_forward(const egs_frame& f, GeomView g, ImgView im, BinView bn, long long cap,
                                   float* out_color, float* out_normal, float* out_depth, float* out_opac, bool save,
                                   cudaStream_t s) {
     const int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
-    static int fwd_bulk = -1;
+    static int fwd_bulk = -1, fwd_pair = 1;
     if (fwd_bulk < 0) {
         const char* e = getenv("EGS_FWD_KERNEL");
         fwd_bulk = (e && e[0] == 'b') ? 1 : 0;
+        fwd_pair = (e && (e[0] == 'b' || e[0] == 'l')) ? 0 : 1;
     }
+    if (fwd_pair && (!save || egs_bwd_variant() == 3))
+        return launch_render_forward2(f, g, im, bn, cap, out_color, out_normal, out_depth, out_opac, save, s);
     if (!save)
         k_render_forward<2><<<gx * gy, EGS_TILE_THREADS, 0, s>>>(f.width, f.height, gx, f.bg, g.rec, im, bn, cap, out_color,
                                                                  out_normal, out_depth, out_opac);

@@ -398,7 +398,7 @@ def test_backward_kernel_variants_agree():
         "np.save(sys.argv[1], o['g_screen'])\n"
     ) % (util.ROOT, os.path.join(util.ROOT, "tests"))
     outs = {}
-    for variant in ("butterfly", "mma", "gather", "warp"):
+    for variant in ("butterfly", "mma", "gather", "warp", "lane"):
         path = "/tmp/egs_variant_%s.npy" % variant
         env = dict(os.environ, EGS_BWD_KERNEL=variant)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=util.ROOT)
@@ -406,11 +406,13 @@ def test_backward_kernel_variants_agree():
     assert rel_err(outs["mma"], outs["butterfly"]) <= 2e-5
     assert rel_err(outs["gather"], outs["butterfly"]) <= 2e-5
     assert rel_err(outs["warp"], outs["butterfly"]) <= 2e-5
+    assert rel_err(outs["lane"], outs["butterfly"]) <= 2e-5
     cam, sc, g, bg, mask, deg, f, b = util.oracle_run("c1_posed_bg")
     sg = util.screen_block_from_oracle(b, sc["xyz"].shape[0])
     assert rel_err(outs["mma"], sg) <= TOL
     assert rel_err(outs["gather"], sg) <= TOL
     assert rel_err(outs["warp"], sg) <= TOL
+    assert rel_err(outs["lane"], sg) <= TOL
 
 
 def test_forward_only_render_matches_and_keeps_no_state():
@@ -464,6 +466,8 @@ def test_tma_staged_variants_are_bit_identical():
             env.update(extra)
             subprocess.run([sys.executable, "-c", code, path, case], check=True, env=env, cwd=util.ROOT)
             outs[name] = np.load(path)
+        # "default" = the two-pixels-per-lane packed-FP32 forward: it keeps the reference's rounding sequence (power,
+        # expf, alpha, transmittance), so it too is bit-identical to the one-pixel-per-lane kernel
         for name in ("fwd_bulk", "sh_bulk", "default"):
             for k in ("color", "depth", "normal", "opacity", "n_contrib", "final_T", "radii"):
                 assert np.array_equal(outs["base"][k], outs[name][k], equal_nan=True), (case, name, k)
