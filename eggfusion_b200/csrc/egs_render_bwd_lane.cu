@@ -3,24 +3,31 @@
 //
 // Same algebra, quirks and inputs as egs_render_bwd_warp.cu (reference: renderCUDA backward, DGS/cuda_rasterizer/
 // backward.cu:419-676; the sigma form is derived in egs_render_bwd.cu): the warp walks its block's hit list
-// {surfel id, pixel mask} back to front in chunks of 32 hits whose 64-byte records are cp.async-staged, double-buffered.
+// {surfel id, pixel mask} back to front in chunks of 32 hits whose 64-byte records are staged by the TMA engine
+// (one cp.async.bulk per record, completing on an mbarrier; SASS UBLKCP / SYNCS), double-buffered.
 // What changes is the cross-pixel reduction.  ncu on the warp variant (round 2, profiles/README.md): the LSU data pipe
 // is 95 % busy -- 30 shared-memory wavefronts per (block, splat) hit, 12 of them the phase-2 gather (lane = splat x
 // pixel-quarter re-reading parked pairs and a per-pixel weight table whose 16-byte entries differ across the warp: 4
 // wavefronts per LDS.128) -- so the kernel is bound by shared-memory wavefronts, not by issue slots or HBM.  Here:
+//   * the records arrive through the TMA engine instead of cp.async: ncu's source page showed every 16-byte LDGSTS of a
+//     gathered record costing one shared-memory wavefront PER LANE (32 per instruction, 5.4 per hit, 21 % of the
+//     kernel's wavefronts); a bulk copy writes shared memory through the async proxy and leaves the LSU pipe alone.
+//     Measured at C3 (bwd_render stage): cp.async 0.712 ms, TMA 0.682 ms, LDG.128 into registers one chunk ahead +
+//     conflict-free STS.128 into a quad-major layout 0.716 ms (the scattered global loads cost the LSU pipe what the
+//     LDGSTS did); the per-lane bulk copies are serialised through uniform registers (~8 issue slots each);
 //   * phase 1 (lane = pixel) parks only {w, u} per (pixel, splat) -- dd = u * (-opacity/2) is a per-splat factor applied
-//     to the finished sums, and "this pixel blended the splat" is recovered as w > 0 -- as two 4-byte stores that put
-//     the pair (even pixel, odd pixel) side by side: 2 wavefronts per hit instead of 4;
+//     to the finished sums, and "this pixel blended the splat" is recovered as w > 0 -- as two conflict-free 4-byte
+//     stores (row = 32 w | 32 u): 2 wavefronts per hit instead of 4;
 //   * phase 2 runs once per 32-hit chunk with lane = splat: every lane walks the 16 pixel pairs of ITS splat's parked
-//     row (one conflict-free LDS.128 per pair) against the block's weight table, which all lanes now read at the same
-//     address (a broadcast: 1 wavefront per LDS.128).  The 14 sums of two horizontally adjacent pixels are accumulated
+//     row (two conflict-free LDS.64 per pair) against the block's weight table, which all lanes now read at the same
+//     address (a broadcast: 2 wavefronts per LDS.128, measured).  The 14 sums of two horizontally adjacent pixels are accumulated
 //     with packed FP32 (FFMA2 / FMUL2 / FADD2 with scalar-broadcast operands), folded once at the end, and the lane
 //     issues its splat's four red.global.add.v4.f32 itself: no shuffles, no second staging of the records, 4 instead
 //     of 12 phase-2 wavefronts and ~13 instead of ~30 phase-2 instructions per hit.
 // A chunk is exactly one phase-2 pass, so the parked rows never outlive their records.
 #include "egs_common.cuh"
 
-#define BL_ROWB 272u        // bytes of one parked row: 16 pixel pairs x {w_even, w_odd, u_even, u_odd} + 16 B pad (bank skew)
+#define BL_ROWB 264u        // bytes of one parked row: w of the 32 pixels | u of the 32 pixels | 8 B pad (bank skew)
 
 namespace {
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
@@ -43,16 +50,17 @@ __device__ __forceinline__ void red_add_f32_l(float* addr, float a) {
 __device__ __forceinline__ void sts32f_l(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void cp_async16_l(uint32_t smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+__device__ __forceinline__ float2 lds64f_l(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
 }
-__device__ __forceinline__ void cp_async_commit_l() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait1_l() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 struct LaneSmem {
-    float4 rec[2][32 * 4];        // records of the chunk being walked / the chunk in flight
+    float4 rec[2][32 * 4];        // records of the chunk being walked / the chunk in flight (TMA destinations)
     uint32_t lm[2][32];           // their blend masks (this block's word)
-    float4 park[32 * 17];         // parked {w, u}: row = hit of the chunk (272 B), unit = pixel pair
+    float2 park[32 * 33];         // parked w | u: row = hit of the chunk (264 B)
+    unsigned long long bar[2];    // mbarriers of the two record buffers
     float4 ktab[16 * 4];          // per pixel pair: {gc0 e,o, gc1 e,o} {gc2 e,o, 10gn0 e,o} {10gn1 e,o, 10gn2 e,o} {gDn e,o, gD e,o}
 };
 } // namespace
@@ -116,22 +124,28 @@ k_render_backward_lane(int W, int H, int gx, const float* __restrict__ bg, const
     };
     const uint32_t rec_smem = smem_addr(S.rec);
     const uint32_t lm_smem = smem_addr(S.lm);
-    // every entry of a hit list has a non-empty mask, so a chunk is dense: slot = lane
-    auto stage_chunk = [&](int buf, uint32_t m, uint32_t idv) {
+    const uint32_t bar_smem = smem_addr(S.bar);
+    if (lane == 0) {
+        mbar_init(bar_smem, 1u);
+        mbar_init(bar_smem + 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // every entry of a hit list has a non-empty mask, so a chunk is dense: slot = lane.  Chunk c lands in buffer c & 1.
+    auto stage_chunk = [&](int c, uint32_t m, uint32_t idv) {
+        const uint32_t buf = (uint32_t)(c & 1);
+        const uint32_t bar = bar_smem + 8u * buf;
+        if (lane == 0) mbar_expect_tx(bar, 64u * (uint32_t)min(32, top - 32 * c));
         if (m != 0u) {
-            const uint32_t slot = (uint32_t)buf * 32u + (uint32_t)lane;
+            const uint32_t slot = buf * 32u + (uint32_t)lane;
             sts32(lm_smem + 4u * slot, m);
-            const float4* src = reinterpret_cast<const float4*>(rec + idv);
-            const uint32_t dst = rec_smem + 64u * slot;
-#pragma unroll
-            for (int q = 0; q < 4; q++) cp_async16_l(dst + 16u * q, src + q);
+            bulk_copy_g2s(rec_smem + 64u * slot, rec + idv, 64u, bar);
         }
     };
 
     uint32_t m_nxt, id_nxt, id_cur;
     load_chunk(0, m_nxt, id_nxt);
     stage_chunk(0, m_nxt, id_nxt);
-    cp_async_commit_l();
     id_cur = id_nxt;
     load_chunk(1, m_nxt, id_nxt);
 
@@ -154,7 +168,7 @@ k_render_backward_lane(int W, int H, int gx, const float* __restrict__ bg, const
     float sigma = 0.f;
     const uint32_t park_base = smem_addr(S.park);
     const uint32_t ktab_base = smem_addr(S.ktab);
-    const uint32_t park_lane = park_base + 16u * (uint32_t)(lane >> 1) + 4u * (uint32_t)(lane & 1);   // this pixel's slot in a row
+    const uint32_t park_lane = park_base + 4u * (uint32_t)lane;   // this pixel's w slot in a row; its u slot is 128 B further
     const uint32_t lanebit = 1u << lane;
     const float fbx = (float)bx, fby = (float)by;
     constexpr float LOG2E = 1.4426950408889634f;
@@ -182,20 +196,23 @@ k_render_backward_lane(int W, int H, int gx, const float* __restrict__ bg, const
         const float dL_dalpha = fmaf(T, kappa, ra * (K0 - sigma));
         sigma = fmaf(w, kappa, sigma);
         sts32f_l(prow, w);
-        sts32f_l(prow + 8u, G * dL_dalpha);       // u; dd = u * (-opacity / 2) is applied to the sums
+        sts32f_l(prow + 128u, G * dL_dalpha);     // u; dd = u * (-opacity / 2) is applied to the sums
     };
 
     for (int c = 0; c < nc; c++) {
         const uint32_t buf = (uint32_t)(c & 1);
         const int cnt = min(32, top - 32 * c);
-        // chunk c+1 -> the other buffer (chunk c-1 is done with it), chunk c+2 -> registers
-        if (c + 1 < nc) stage_chunk((int)(buf ^ 1u), m_nxt, id_nxt);
-        cp_async_commit_l();
+        // phase 2 of chunk c-1 is done with the parked rows and with the other record buffer (generic-proxy reads):
+        // order them before the async-proxy writes of the copies issued next
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // chunk c+1 -> the other buffer, chunk c+2 -> registers
+        if (c + 1 < nc) stage_chunk(c + 1, m_nxt, id_nxt);
         const uint32_t id_mine = id_cur;      // surfel of hit `lane` of this chunk
         id_cur = id_nxt;
         load_chunk(c + 2, m_nxt, id_nxt);
-        cp_async_wait1_l();   // chunk c has landed (this thread's copies) ...
-        __syncwarp();         // ... and everybody else's; also: phase 2 of chunk c-1 is done with the parked rows
+        mbar_wait(bar_smem + 8u * buf, (uint32_t)((c >> 1) & 1));   // chunk c has landed
+        __syncwarp();                                               // ... and everybody's mask words are visible
 
         const uint32_t rec_base = rec_smem + 2048u * buf;
         const uint32_t lm_base = lm_smem + 128u * buf;
@@ -229,12 +246,12 @@ k_render_backward_lane(int W, int H, int gx, const float* __restrict__ bg, const
             float2 s_c0 = s_ux, s_c1 = s_ux, s_c2 = s_ux, s_n0 = s_ux, s_n1 = s_ux, s_n2 = s_ux, s_d = s_ux;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                const float4 pr = lds128(row + 16u * (uint32_t)j);                 // w even, w odd, u even, u odd
+                const float2 w2 = lds64f_l(row + 8u * (uint32_t)j);                // w even, w odd
+                const float2 u2 = lds64f_l(row + 128u + 8u * (uint32_t)j);         // u even, u odd
                 const float4 k0 = lds128(ktab_base + 64u * (uint32_t)j);            // broadcasts
                 const float4 k1 = lds128(ktab_base + 64u * (uint32_t)j + 16u);
                 const float4 k2 = lds128(ktab_base + 64u * (uint32_t)j + 32u);
                 const float4 k3 = lds128(ktab_base + 64u * (uint32_t)j + 48u);
-                const float2 w2 = make_float2(pr.x, pr.y), u2 = make_float2(pr.z, pr.w);
                 const float lx = (float)(2 * (j & 3)), ly = (float)(j >> 2);
                 const float2 dx2 = __fadd2_rn(bc2(xr), make_float2(-lx, -lx - 1.f));
                 const float dy = yr - ly;
@@ -246,7 +263,7 @@ k_render_backward_lane(int W, int H, int gx, const float* __restrict__ bg, const
                 s_yy = __ffma2_rn(udy, bc2(dy), s_yy);
                 s_u = __fadd2_rn(s_u, u2);
                 // 1 where the pixel blended the splat (w >= alpha_min * T_min = 4e-7), else 0
-                const float2 act = make_float2(__saturatef(pr.x * 1e30f), __saturatef(pr.y * 1e30f));
+                const float2 act = make_float2(__saturatef(w2.x * 1e30f), __saturatef(w2.y * 1e30f));
                 s_gd = __ffma2_rn(make_float2(k3.z, k3.w), act, s_gd);
                 s_c0 = __ffma2_rn(make_float2(k0.x, k0.y), w2, s_c0);
                 s_c1 = __ffma2_rn(make_float2(k0.z, k0.w), w2, s_c1);
