@@ -109,6 +109,15 @@ def make_workload(name):
     return scene, cams, grads, deg
 
 
+def config_dict(workload, P, W, H, deg, M, instances):
+    """`config` of the JSON line: the SAME dict in both arms (the driver compares them)."""
+    return {"workload": "%s: %d surfels @%dx%d, SH degree %d, 4 cameras cycled, 'layers' scene seed %d"
+                        % (workload, P, W, H, deg, 20251201),
+            "l2_policy": "inputs larger than L2 (params %.0f MB + records %.0f MB per step; 126 MB L2)"
+                         % (P * (44 + 12 * M) / 1e6, 64 * P / 1e6),
+            "instances_per_frame": float(instances)}
+
+
 def algorithmic_bytes(P, P_vis, I, N_px, M):
     """bytes each stage must move at least once."""
     b = {
@@ -463,7 +472,7 @@ def cpu_baseline_sample(scene, cams, grads, deg, budget_s=12.0):
             break
     dt = time.perf_counter() - t0
     return {"value": 256.0 * I_tot / dt / 1e6, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "frames_per_s": frames / dt,
+            "frames_per_s": frames / dt, "instances_per_frame": I_tot / frames,
             "sample": "%d full frame(s) fwd+bwd (cameras 0..%d, %d instances) in %.1f s" % (frames, frames - 1, I_tot, dt)}
 
 
@@ -583,7 +592,7 @@ def run_ours(args):
     value = 256.0 * I_total / (ms_step * 1e-3) / 1e6
 
     # ---- e2e through the public API, host buffers in the timed region (rank-local tiles when sharded)
-    e2e = None
+    e2e, e2e_eager = None, None
     if not args.no_e2e:
         tgt_host = [(torch.from_numpy(np.random.default_rng(7 + i).uniform(0, 1, (3, H, W)).astype(np.float32)).pin_memory(),
                      torch.from_numpy(np.random.default_rng(70 + i).uniform(1, 3, (1, H, W)).astype(np.float32)).pin_memory())
@@ -592,44 +601,94 @@ def run_ours(args):
                      torch.from_numpy(c.campos.copy()).pin_memory()) for c in cams]
         leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         h2d = 4 * (4 * H * W) + 4 * (16 + 16 + 3)
-        losses = []
         feeder = HostFeeder(cam_host, tgt_host, dev)
         # the library's steady-state setting for optimisation loops: binning capacity from the recent instance
         # counts instead of a blocking read-back per forward (overflow is still detected, one call late)
         R.config.capacity = "auto"
+        c0 = cams[0]
+        # static device tensors the step reads: a step's inputs are copied into them (H2D from pinned memory on a side
+        # stream one step ahead, then device-to-device here), so the same recorded step serves every camera
+        st_view, st_proj, st_campos = (torch.empty_like(x, device=dev) for x in cam_host[0])
+        st_tc, st_td = (torch.empty_like(x, device=dev) for x in tgt_host[0])
+        s_static = E.GaussianRasterizationSettings(H, W, c0.tanfovx, c0.tanfovy, bg, 1.0, st_view, st_proj, deg, st_campos,
+                                                   False, False, c0.cx, c0.cy)
 
-        def e2e_step(i):
-            ci = i % len(cams)
-            c = cams[ci]
-            view, proj, campos, tc, td = feeder.get(i)
-            s = E.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, view, proj, deg, campos, False,
-                                                False, c.cx, c.cy)
-            color, normal, depth, opac, _a, _r = E.GaussianRasterizer(s)(
+        def api_step():
+            """The call a user makes: the reference-facing rasterizer + a torch loss + loss.backward()."""
+            color, normal, depth, opac, _a, _r = E.GaussianRasterizer(s_static)(
                 means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
                 rotations=leaf["rotations"], tile_mask=mask)
-            loss = (color - tc).abs().mean() + (depth - td).abs().mean() + 0.1 * (1 - normal[2]).mean()
+            loss = (color - st_tc).abs().mean() + (depth - st_td).abs().mean() + 0.1 * (1 - normal[2]).mean()
             loss.backward()
+            return loss
+
+        def load_inputs(i):
+            for dst, src in zip((st_view, st_proj, st_campos, st_tc, st_td), feeder.get(i)):
+                dst.copy_(src, non_blocking=True)
+
+        def eager_step(i):
+            load_inputs(i)
             for v in leaf.values():
                 v.grad = None
-            losses.append(loss.item())  # D2H of the step's result
-        nw = max(3, args.warmup)
-        for i in range(nw):
-            e2e_step(i)
-        barrier()
-        n_e2e = args.steps
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(nw, nw + n_e2e):
-            e2e_step(i)
-        b.record()
-        barrier()
-        t_e2e = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t_e2e.item()) / n_e2e
-        e2e = {"value": 256.0 * I_total / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e,
-               "frames_per_s": 1e3 / ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 16,
-               "api": "eggfusion_b200.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"}
+            return float(api_step())      # D2H of the step's result
+
+        def time_e2e(fn):
+            nw = max(3, args.warmup)
+            for i in range(nw):
+                fn(i)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(nw, nw + args.steps):
+                fn(i)
+            b.record()
+            barrier()
+            t_ = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item()) / args.steps
+
+        def line_e2e(ms, api):
+            return {"value": 256.0 * I_total / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+                    "frames_per_s": 1e3 / ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "api": api}
+        ms_eager = time_e2e(eager_step)
+        e2e_eager = line_e2e(ms_eager, "eggfusion_b200.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item(), "
+                                       "eager (every call enqueued from Python each step)")
+        e2e = e2e_eager
+        if world == 1 and not args.no_graph:
+            # The same calls recorded ONCE into a CUDA graph (torch.cuda.graph) and replayed per step: possible because
+            # the rasterizer never talks to the host in its steady state (the reference reads the instance count back
+            # twice per forward, rasterizer_impl.cu:311,349-366, and cannot be captured).  Per step: inputs H2D + copied
+            # into the static tensors, one replay, loss.item().
+            for v in leaf.values():
+                v.grad = None
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    float(api_step())
+                    for v in leaf.values():
+                        v.grad = None
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss_static = api_step()
+
+            def graph_step(i):
+                load_inputs(i)
+                graph.replay()
+                return float(loss_static)
+            # same numbers as the eager path on the same inputs
+            l_g = graph_step(5)
+            g_g = leaf["xyz"].grad.clone()
+            l_e = eager_step(5)
+            assert abs(l_g - l_e) <= 1e-6 * abs(l_e), (l_g, l_e)
+            assert float((leaf["xyz"].grad - g_g).abs().max()) <= 1e-5 * float(g_g.abs().max())
+            ms_graph = time_e2e(graph_step)
+            R.check_captured(clear=True)      # no binning overflow in any replay (reads the device counters)
+            e2e = line_e2e(ms_graph, "eggfusion_b200.GaussianRasterizer + torch L1 loss + loss.backward() recorded once with "
+                                     "torch.cuda.graph, replayed per step + loss.item(); inputs H2D from pinned memory per step")
+            del graph
 
     mapping = None
     if world == 1 and not args.no_mapping:
@@ -685,18 +744,20 @@ def run_ours(args):
     dom_stage = max((k for k in stage_ms if k in ("plan", "render", "bwd_render", "bwd_surfels")),
                     key=lambda k: stage_ms[k])
     if dom_stage == "render":
-        dom_kernel, dom_bytes = "k_render_forward(+k_emit,k_tile_sort)", ab["emit_sort"] + ab["render_forward"]
+        dom_kernel, dom_bytes = "k_render_forward2(+k_emit,k_tile_sort)", ab["emit_sort"] + ab["render_forward"]
     else:
         dom_kernel, dom_bytes = "k_" + kern_of[dom_stage], ab[kern_of[dom_stage]]
         if dom_stage == "bwd_render":
-            dom_kernel = "k_render_backward_" + os.environ.get("EGS_BWD_KERNEL", "warp")
+            dom_kernel = "k_render_backward_" + os.environ.get("EGS_BWD_KERNEL", "lane")
     achieved = dom_bytes / (stage_ms[dom_stage] * 1e-3) / 1e9
     traffic, issue = None, None
     try:  # DRAM bytes / warp instructions of the same kernel from the committed ncu capture of this workload (profiles/)
         nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = nt[args.workload].get(dom_kernel)
         winst = nt.get("_warp_instructions", {}).get(args.workload, {}).get(dom_kernel)
-        if winst and clocks.get("sm_mhz"):
+        if world > 1:
+            traffic = None      # the committed capture is a whole single-GPU frame: not this rank's share
+        if winst and clocks.get("sm_mhz") and world == 1:
             # the bound that actually limits the compositing kernels: warp-instruction issue, 4 schedulers x 148 SMs
             peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
             issue = {"warp_instructions": winst, "achieved_per_s": winst / (stage_ms[dom_stage] * 1e-3),
@@ -706,14 +767,10 @@ def run_ours(args):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d surfels @%dx%d, SH degree %d, 4 cameras cycled, 'layers' scene seed %d"
-                               % (args.workload, P, W, H, deg, 20251201),
-                   "l2_policy": "inputs larger than L2 (params %.0f MB + records %.0f MB per step; 126 MB L2)"
-                                % (P * (44 + 12 * M) / 1e6, 64 * P / 1e6),
-                   "parallelism": "tiles%d" % world if world > 1 else "single",
-                   "instances_per_frame": I_total, "visible_surfels": vis_mean},
+        "config": config_dict(args.workload, P, W, H, deg, M, I_total),
+        "parallelism": "tiles%d" % world if world > 1 else "single", "visible_surfels": vis_mean,
         "frames_per_s": 1e3 / ms_step,
         "nominal_surfel_pixels_per_s_M": P * N_px / (ms_step * 1e-3) / 1e6,
         "stage_ms": stage_ms,
@@ -726,6 +783,7 @@ def run_ours(args):
         "clocks": clocks,
         "gpu_launches": 7 * args.steps * world,
         "e2e": e2e,
+        "e2e_eager": e2e_eager,
         "mapping_iter": mapping,
         "tracking_frame": tracking,
     }
@@ -755,9 +813,10 @@ def run_reference(args):
         # no compiled reference on this box: time the CPU port of its algorithm on a bounded sample
         cb = cpu_baseline_sample(scene, cams, grads, deg)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
-                          "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                          "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": args.workload}, "cpu_baseline": cb,
+                          "config": config_dict(args.workload, P, W, H, deg, M, cb.get("instances_per_frame", 0.0)),
+                          "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}))
         return
@@ -870,10 +929,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "device": "cuda (unmodified diff-gaussian-surfels compiled for sm_100a, oracle/_ref)",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "%s: %d surfels @%dx%d, SH degree %d, 4 cameras cycled" % (args.workload, P, W, H, deg),
-                   "instances_per_frame": I_mean},
+        "config": config_dict(args.workload, P, W, H, deg, M, I_mean),
         "frames_per_s": 1e3 / ms_step, "clocks": clocks,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                          "sample": "full workload; the reference has no CPU implementation of this path, so its own "
@@ -896,6 +954,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e: eager calls only (no torch.cuda.graph replay)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mapping", action="store_true")
     ap.add_argument("--no-tracking", action="store_true")

@@ -96,6 +96,29 @@ def _get_pinned():
 
 
 _auto_history = {}      # (device index, P, W, H) -> recent instance counts ("auto" capacity)
+_captured = []          # counter words of forwards recorded into a CUDA graph (checked by check_captured())
+
+
+def _capturing() -> bool:
+    return torch.cuda.is_current_stream_capturing()
+
+
+def check_captured(clear: bool = False):
+    """Forwards recorded into a CUDA graph (torch.cuda.graph) cannot report a binning overflow themselves: nothing in
+    a graph may talk to the host.  Call this after a replay (it synchronises the device): raises if any captured
+    forward produced more instances than its capacity; returns the list of (num_rendered, tile_num, overflow,
+    num_visible) tuples otherwise."""
+    out = []
+    for words, cap in _captured:
+        c = tuple(int(v) for v in words.cpu())
+        if c[2] != 0:
+            raise RuntimeError(
+                f"eggsplat: a graph-captured forward produced {c[0]} instances but the binning workspace was sized for "
+                f"{cap}; its lists were truncated. Re-capture with a larger eggfusion_b200.rasterizer.config.capacity.")
+        out.append(c)
+    if clear:
+        _captured.clear()
+    return out
 
 
 def _auto_note(key, count: int):
@@ -175,7 +198,9 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
     P = means3D.size(0)
     H, W = int(settings.image_height), int(settings.image_width)
     with torch.cuda.device(device):
-        _check_pending()
+        capturing = _capturing()
+        if not capturing:
+            _check_pending()
         stream = _stream_ptr(device)
         means3D = _f32c(means3D, device)
         use_sh = _present(shs)
@@ -214,7 +239,12 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
             hist = _auto_history.get(auto_key)
             capacity = "exact" if not hist else int(max(hist) * config.auto_headroom) + config.auto_slack
         exact = capacity == "exact"
-        host = _get_pinned()
+        if capturing and exact:
+            raise RuntimeError(
+                "eggsplat: a forward recorded into a CUDA graph needs a fixed binning capacity (no host read-back is "
+                "possible inside a graph): set eggfusion_b200.rasterizer.config.capacity to an int, or to 'auto' and "
+                "run one eager forward of this shape first")
+        host = None if capturing else _get_pinned()
         _lib.check(lib.egs_forward_plan(C.byref(frame), _ptr(means3D), _ptr(shs) if use_sh else None,
                                         None if use_sh else _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
                                         _ptr(rotations), _ptr(tile_mask), st.geom.data_ptr(), st.img.data_ptr(),
@@ -235,9 +265,11 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
         _lib.check(lib.egs_forward_render(C.byref(frame), _ptr(tile_mask), _ptr(radii), st.geom.data_ptr(),
                                           st.img.data_ptr(), st.bin.data_ptr(), st.cap, color.data_ptr(),
                                           normal.data_ptr(), depth.data_ptr(), opac.data_ptr(),
-                                          None if exact else host.data_ptr(), 0 if save else _lib.EGS_FWD_NO_SAVE,
-                                          stream), "forward_render")
-        if not exact:
+                                          None if (exact or capturing) else host.data_ptr(),
+                                          0 if save else _lib.EGS_FWD_NO_SAVE, stream), "forward_render")
+        if capturing:
+            _captured.append((st.img[:16].view(torch.int32), st.cap))
+        elif not exact:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
             _pending_overflow.append((ev, host, st.cap, auto_key))
@@ -254,6 +286,11 @@ def backward_raw(st: ForwardState, means3D, shs, colors_precomp, scales, rotatio
     if not getattr(st, "saved", True):
         raise RuntimeError("eggsplat: this forward was a forward-only render (save=False / no_grad): no backward state")
     with torch.cuda.device(device):
+        if st.num_rendered == -1 and not _capturing():
+            # the forward ran without a host read-back: if its counters have arrived by now (they usually have: the
+            # loss was enqueued in between) an overflow is raised HERE, before any gradient of the truncated lists
+            # reaches an optimiser; otherwise at the next forward (one step late, documented in _Config)
+            _check_pending()
         stream = _stream_ptr(device)
         f32 = dict(dtype=torch.float32, device=device)
         means3D = _f32c(means3D, device)

@@ -260,9 +260,12 @@ def test_fixed_capacity_mode_and_overflow_detection():
     assert np.array_equal(roomy["color"], exact["color"])
     assert np.array_equal(roomy["point_list"][:exact["num_rendered"]], exact["point_list"])
     R._check_pending(block=True)
-    cuda_run(name, capacity=max(1, exact["num_rendered"] // 2))
+    # the overflow is raised by the backward of the same step when the counters have arrived by then (before any
+    # gradient of the truncated lists exists), at the latest by the next forward / an explicit blocking check
     with pytest.raises(RuntimeError, match="truncated"):
+        cuda_run(name, capacity=max(1, exact["num_rendered"] // 2))
         R._check_pending(block=True)
+    R._pending_overflow.clear()
 
 
 def test_auto_capacity_policy():
@@ -285,9 +288,10 @@ def test_auto_capacity_policy():
     R._auto_history[key] = [max(1, exact["num_rendered"] // 4)]
     slack, R.config.auto_slack = R.config.auto_slack, 0
     try:
-        cuda_run(name, capacity="auto")
         with pytest.raises(RuntimeError, match="truncated"):
+            cuda_run(name, capacity="auto")
             R._check_pending(block=True)
+        R._pending_overflow.clear()
     finally:
         R.config.auto_slack = slack
         R._auto_history.clear()
@@ -680,3 +684,92 @@ def test_live_reference_at_headline_sizes(workload):
     assert torch.equal(img, O["color"])
     assert _rel_t(acc, full_sg) <= 1e-5
     assert _frac_close_t(acc, full_sg, rtol=1e-4, atol_rel=1e-5) >= 0.9999
+
+
+def test_public_api_records_into_a_cuda_graph():
+    """GaussianRasterizer + a torch loss + loss.backward() recorded once with torch.cuda.graph and replayed: same loss and
+    gradients as the eager calls, new cameras through static tensors, overflow of a captured forward reported by
+    check_captured().  (The reference cannot be captured: it reads the instance count back to the host twice per
+    forward, rasterizer_impl.cu:311,349-366.)"""
+    import eggfusion_b200 as E
+    from eggfusion_b200 import rasterizer as R, synthetic as syn
+    cam, sc, g, bg, mask, deg = util.case_inputs("c1_posed_bg")
+    cam2 = syn.default_camera(cam.width, cam.height, syn.look_from((0.05, 0.02, -0.03), -0.04, 0.03))
+    view, proj, campos = _t(cam.viewmatrix), _t(cam.projmatrix), _t(cam.campos)
+    s = E.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, _t(bg), 1.0, view, proj, deg,
+                                        campos, False, False, cam.cx, cam.cy)
+    leaf = {k: _t(sc[k]).requires_grad_(True) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
+    tc = torch.rand(3, cam.height, cam.width, device=DEV)
+
+    def step():
+        color, normal, depth, opac, _a, _r = E.GaussianRasterizer(s)(
+            means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
+            rotations=leaf["rotations"])
+        loss = (color - tc).abs().mean() + depth.mean() + 0.1 * (1 - normal[2]).mean() + (opac * opac).mean()
+        loss.backward()
+        return loss
+
+    def eager():
+        for v in leaf.values():
+            v.grad = None
+        l = float(step())
+        return l, {k: v.grad.clone() for k, v in leaf.items()}
+    old = R.config.capacity
+    R._captured.clear()
+    try:
+        R.config.capacity = "exact"
+        with pytest.raises(RuntimeError, match="fixed binning capacity"):
+            gtmp = torch.cuda.CUDAGraph()
+            for v in leaf.values():
+                v.grad = None
+            with torch.cuda.graph(gtmp):
+                step()
+        torch.cuda.synchronize()
+        l1, g1 = eager()
+        R.config.capacity = int(1.2 * R.forward_raw(s, leaf["xyz"].detach(), leaf["shs"].detach(), torch.Tensor([]),
+                                                    leaf["opacity"].detach(), leaf["scales"].detach(),
+                                                    leaf["rotations"].detach(), None)[6].num_rendered) + 64
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for v in leaf.values():
+                v.grad = None
+            float(step())
+        torch.cuda.current_stream().wait_stream(side)
+        for v in leaf.values():
+            v.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_static = step()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert abs(float(loss_static) - l1) <= 1e-6 * abs(l1)
+        for k in leaf:
+            assert rel_err(leaf[k].grad.cpu().numpy(), g1[k].cpu().numpy()) <= 1e-5, k
+        counters = R.check_captured()
+        assert len(counters) == 1 and counters[0][2] == 0 and counters[0][0] > 0
+        # another camera through the same recorded step
+        view.copy_(_t(cam2.viewmatrix)); proj.copy_(_t(cam2.projmatrix)); campos.copy_(_t(cam2.campos))
+        graph.replay()
+        torch.cuda.synchronize()
+        lg, gg = float(loss_static), {k: v.grad.clone() for k, v in leaf.items()}
+        R.config.capacity = "exact"
+        le, ge = eager()
+        assert abs(lg - le) <= 1e-6 * abs(le) and abs(le - l1) > 1e-4 * abs(l1)
+        for k in leaf:
+            assert rel_err(gg[k].cpu().numpy(), ge[k].cpu().numpy()) <= 1e-5, k
+        # a capacity that is too small is reported (not silently truncated) by check_captured()
+        R._captured.clear()
+        R.config.capacity = max(1, counters[0][0] // 3)
+        for v in leaf.values():
+            v.grad = None
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            step()
+        g2.replay()
+        with pytest.raises(RuntimeError, match="truncated"):
+            R.check_captured()
+    finally:
+        R.config.capacity = old
+        R._captured.clear()
+        torch.cuda.synchronize()
