@@ -41,6 +41,8 @@ SIGNATURES = {
                                       C.POINTER(C.c_size_t)]),
     "egs_bin_bytes_forward_only": (C.c_int, [_I64, C.POINTER(C.c_size_t)]),
     "egs_forward_plan": (C.c_int, [C.POINTER(Frame)] + [_P] * 13),
+    "egs_forward_plan_sharded": (C.c_int, [C.POINTER(Frame)] + [_P] * 7 + [_I32, _I32] + [_P] * 6),
+    "egs_push_rows": (C.c_int, [_I32, _I32, _P, _P, _P, _P]),
     "egs_forward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),
     "egs_backward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),
     "egs_backward_surfels": (C.c_int, [C.POINTER(Frame), _I32, _I32] + [_P] * 17),
@@ -90,6 +92,7 @@ class AdamHyper(C.Structure):
 EGM_TERMS, EGM_REG = 8, 4
 SIGNATURES.update({
     "egm_loss_seed": (C.c_int, [_I32, _I32] + [_P] * 8 + [C.c_float] * 3 + [_P] * 5),
+    "egm_loss_seed_tiles": (C.c_int, [_I32, _I32] + [_P] * 9 + [C.c_float] * 3 + [_P] * 5),
     "egm_adam_step": (C.c_int, [_I32, _I32, C.POINTER(AdamHyper)] + [_P] * 27),
     "egm_activate": (C.c_int, [_I32] + [_P] * 8),
     "egm_loss_total": (C.c_int, [_P, _P, _I32, _I32] + [C.c_float] * 5 + [_I32, _I32, _P, _P]),

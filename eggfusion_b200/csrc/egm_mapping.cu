@@ -94,7 +94,8 @@ k_loss_seed(long long n, const float* __restrict__ est_color, const float* __res
             const float* __restrict__ est_normal, const float* __restrict__ ref_color,
             const float* __restrict__ ref_depth, const float* __restrict__ ref_normal,
             const uint8_t* __restrict__ rgb_mask, const uint8_t* __restrict__ geo_mask, float cw, float dw, float nw,
-            float* __restrict__ g_color, float* __restrict__ g_depth, float* __restrict__ g_normal, double* terms) {
+            float* __restrict__ g_color, float* __restrict__ g_depth, float* __restrict__ g_normal, double* terms,
+            const int32_t* __restrict__ tile_mask, int width, int tiles_x) {
     const double cnt = terms[EGM_T_COUNT];
     // mean backward: grad / numel of the indexed tensor ([n,3] colour, [n,1] depth, [n] cosine distance)
     const float up_c = cnt > 0.0 ? (float)((double)cw / (3.0 * cnt)) : 0.f;
@@ -133,6 +134,14 @@ k_loss_seed(long long n, const float* __restrict__ est_color, const float* __res
                 p[j].ed = d.f[j]; p[j].rd = rdv.f[j];
                 p[j].m = ((m0 >> (8 * j)) & 0xffu) != 0u && ((m1 >> (8 * j)) & 0xffu) != 0u;
             }
+            if (tile_mask) {   // a rank of a tile-sharded frame: only the pixels of its own tiles take part
+                const int y = (int)(i0 / width), x = (int)(i0 - (long long)y * width);   // n % 4 == 0 and aligned rows: the 4 pixels share a tile when width % 4 == 0
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int xx = x + j, yy = y + (xx >= width ? 1 : 0), xw = xx >= width ? xx - width : xx;
+                    p[j].m = p[j].m && __ldg(tile_mask + (yy >> 4) * tiles_x + (xw >> 4)) != 0;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) loss_pixel(p[j], have_depth, have_normal, up_c, up_d, up_n, acc, o[j]);
 #pragma unroll
@@ -153,6 +162,10 @@ k_loss_seed(long long n, const float* __restrict__ est_color, const float* __res
             p[0].ed = est_depth[i];
             p[0].rd = ref_depth ? ref_depth[i] : 0.f;
             p[0].m = rgb_mask[i] != 0 && (geo_mask == nullptr || geo_mask[i] != 0);
+            if (tile_mask) {
+                const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+                p[0].m = p[0].m && __ldg(tile_mask + (y >> 4) * tiles_x + (x >> 4)) != 0;
+            }
             loss_pixel(p[0], have_depth, have_normal, up_c, up_d, up_n, acc, o[0]);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
@@ -390,6 +403,16 @@ EGS_API int egm_loss_seed(int32_t height, int32_t width, const float* est_color,
                           const float* ref_normal, const uint8_t* rgb_mask, const uint8_t* geo_mask,
                           float color_weight, float depth_weight, float normal_weight, float* dL_dcolor,
                           float* dL_ddepth, float* dL_dnormal, double* terms, void* stream) {
+    return egm_loss_seed_tiles(height, width, est_color, est_depth, est_normal, ref_color, ref_depth, ref_normal, rgb_mask,
+                               geo_mask, nullptr, color_weight, depth_weight, normal_weight, dL_dcolor, dL_ddepth,
+                               dL_dnormal, terms, stream);
+}
+
+EGS_API int egm_loss_seed_tiles(int32_t height, int32_t width, const float* est_color, const float* est_depth,
+                                const float* est_normal, const float* ref_color, const float* ref_depth,
+                                const float* ref_normal, const uint8_t* rgb_mask, const uint8_t* geo_mask,
+                                const int32_t* tile_mask, float color_weight, float depth_weight, float normal_weight,
+                                float* dL_dcolor, float* dL_ddepth, float* dL_dnormal, double* terms, void* stream) {
     if (height <= 0 || width <= 0) return EGS_E_BADARG;
     if (!est_color || !est_depth || !est_normal || !ref_color || !rgb_mask || !dL_dcolor || !dL_ddepth || !dL_dnormal ||
         !terms)
@@ -408,12 +431,13 @@ EGS_API int egm_loss_seed(int32_t height, int32_t width, const float* est_color,
         k_loss_seed<4><<<grid_for(n / 4, 256, 1 << 30), 256, 0, s>>>(n, est_color, est_depth, est_normal, ref_color,
                                                                    ref_depth, ref_normal, rgb_mask, geo_mask,
                                                                    color_weight, depth_weight, normal_weight, dL_dcolor,
-                                                                   dL_ddepth, dL_dnormal, terms);
+                                                                   dL_ddepth, dL_dnormal, terms, tile_mask, width,
+                                                                   (width + 15) / 16);
     else
         k_loss_seed<1><<<grid_for(n, 256, 1 << 30), 256, 0, s>>>(n, est_color, est_depth, est_normal, ref_color,
                                                                ref_depth, ref_normal, rgb_mask, geo_mask, color_weight,
                                                                depth_weight, normal_weight, dL_dcolor, dL_ddepth,
-                                                               dL_dnormal, terms);
+                                                               dL_dnormal, terms, tile_mask, width, (width + 15) / 16);
     EGM_TRY(cudaGetLastError());
     return 0;
 }

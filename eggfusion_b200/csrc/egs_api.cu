@@ -3,7 +3,8 @@
 #include "egs_common.cuh"
 
 cudaError_t launch_surfel_forward(const egs_frame&, const float*, const float*, const float*, const float*, const float*,
-                                  const float*, const int32_t*, GeomView, ImgView, int32_t*, uint8_t*, cudaStream_t);
+                                  const float*, const int32_t*, GeomView, ImgView, int32_t*, uint8_t*, int, int,
+                                  cudaStream_t);
 cudaError_t launch_surfel_backward(const egs_frame&, int, int, const float*, const float*, const float*, const float*,
                                    const float*, const int32_t*, GeomView, const float*, float*, float*, float*, float*,
                                    float*, float*, float*, float*, cudaStream_t);
@@ -39,6 +40,27 @@ inline int check_frame(const egs_frame* f) {
         cudaError_t e__ = (expr);                  \
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)
+
+// Exchange step of a tile-sharded frame, over NVLink peer memory instead of a dense reduce-scatter.
+// One thread per (surfel, 16-byte quad of its screen-gradient row).  A surfel that touched one of this rank's tiles
+// (tiles_touched != 0; at 8 GPUs ~1/5 of the visible ones) has a partial row in the rank's local block: the thread adds
+// its quad to the OWNER's accumulation block with one red.global.add.v4.f32 on the owner's (peer-mapped) address and
+// clears the local quad, so the local block is all zeros again for the next step (no memset).  Rows nobody touched
+// cost a 4-byte read.  peer_base[r] = rank r's accumulation block for its surfel range [r*chunk, (r+1)*chunk).
+__global__ void __launch_bounds__(256)
+k_push_rows(int P, int chunk, const uint32_t* __restrict__ tiles_touched, float* __restrict__ local_sg,
+            float* const* __restrict__ peer_base) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int i = (int)(t >> 2), q = (int)(t & 3);
+    if (i >= P || tiles_touched[i] == 0u) return;
+    float4* src = reinterpret_cast<float4*>(local_sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i) + q;
+    const float4 v = *src;
+    *src = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
+    const int owner = i / chunk;
+    float* dst = peer_base[owner] + (size_t)EGS_SCREEN_GRAD_STRIDE * (i - owner * chunk) + 4 * q;
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __global__ void k_export_ranges(ImgView im, int tiles, uint32_t* ranges, int32_t* tile_indices) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,6 +105,15 @@ EGS_API int egs_forward_plan(const egs_frame* f, const float* means3D, const flo
                      const float* opacities, const float* scales, const float* rotations, const int32_t* tile_mask,
                      void* geom, void* img, int32_t* radii, uint8_t* active_mask, egs_counters* counters_host,
                      void* stream) {
+    return egs_forward_plan_sharded(f, means3D, shs, colors_precomp, opacities, scales, rotations, tile_mask, 0,
+                                    f ? f->num_surfels : 0, geom, img, radii, active_mask, counters_host, stream);
+}
+
+EGS_API int egs_forward_plan_sharded(const egs_frame* f, const float* means3D, const float* shs,
+                                     const float* colors_precomp, const float* opacities, const float* scales,
+                                     const float* rotations, const int32_t* tile_mask, int32_t own_first,
+                                     int32_t own_count, void* geom, void* img, int32_t* radii, uint8_t* active_mask,
+                                     egs_counters* counters_host, void* stream) {
     int rc = check_frame(f);
     if (rc) return rc;
     if (!img) return EGS_E_BADARG;
@@ -98,8 +129,9 @@ EGS_API int egs_forward_plan(const egs_frame* f, const float* means3D, const flo
         if (!shs && !colors_precomp) return EGS_E_BADARG;
         if (!colors_precomp && f->sh_coeffs < (f->sh_degree + 1) * (f->sh_degree + 1)) return EGS_E_BADARG;
         GeomView g = carve_geom(geom, (size_t)P);
+        if (own_first < 0 || own_count < 0 || own_first + own_count > P) return EGS_E_BADARG;
         EGS_TRY(launch_surfel_forward(*f, means3D, scales, rotations, opacities, shs, colors_precomp, tile_mask, g, im,
-                                      radii, active_mask, s));
+                                      radii, active_mask, own_first, own_count, s));
     }
     EGS_TRY(launch_tile_scan(im, tiles, -1, s));
     if (counters_host) EGS_TRY(cudaMemcpyAsync(counters_host, im.counters, sizeof(egs_counters), cudaMemcpyDeviceToHost, s));
@@ -168,6 +200,19 @@ EGS_API int egs_backward_surfels(const egs_frame* f, int32_t first, int32_t coun
     EGS_TRY(launch_surfel_backward(*f, first, count, means3D, shs, colors_precomp, scales, rotations, radii, g,
                                    screen_grads, dL_dmeans3D, dL_dopacity, dL_dsh, dL_dscales, dL_drotations,
                                    dL_dmeans2D, dL_dcolors, dL_dcov3D, (cudaStream_t)stream));
+    return 0;
+}
+
+EGS_API int egs_push_rows(int32_t P, int32_t chunk_rows, const void* geom, float* local_screen_grads,
+                          float* const* peer_blocks, void* stream) {
+    if (P < 0 || chunk_rows <= 0) return EGS_E_BADARG;
+    if (P == 0) return 0;
+    if (!geom || !local_screen_grads || !peer_blocks) return EGS_E_BADARG;
+    GeomView g = carve_geom(const_cast<void*>(geom), (size_t)P);
+    const long long threads = 4ll * P;
+    k_push_rows<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, chunk_rows, g.tiles_touched,
+                                                                                     local_screen_grads, peer_blocks);
+    EGS_TRY(cudaGetLastError());
     return 0;
 }
 

@@ -65,11 +65,14 @@ __global__ void __launch_bounds__(1024) k_tile_scan(ImgView im, int tiles, long 
 // ---- 3. emit -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_emit(int P, int gx, int gy, const int32_t* __restrict__ radii, const SplatRecord* __restrict__ rec,
-       const int32_t* __restrict__ tile_mask, ImgView im, BinView bn, long long cap) {
+       const uint32_t* __restrict__ tiles_touched, const int32_t* __restrict__ tile_mask, ImgView im, BinView bn,
+       long long cap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const int r = radii[i];
     if (r <= 0) return;
+    // nothing to emit (all its tiles are masked out); in a sharded frame such a surfel may not even have a record
+    if (tiles_touched[i] == 0u) return;
     const float4 q0 = __ldg(reinterpret_cast<const float4*>(rec + i));
     const float depth = __ldg(&rec[i].depth);
     int x0, y0, x1, y1;
@@ -244,7 +247,7 @@ cudaError_t launch_tile_scan(ImgView im, int tiles, long long cap, cudaStream_t 
 cudaError_t launch_emit_sort(int P, int gx, int gy, const int32_t* radii, GeomView g, const int32_t* tile_mask,
                              ImgView im, BinView bn, long long cap, cudaStream_t s) {
     if (P == 0) return cudaSuccess;
-    k_emit<<<(P + 255) / 256, 256, 0, s>>>(P, gx, gy, radii, g.rec, tile_mask, im, bn, cap);
+    k_emit<<<(P + 255) / 256, 256, 0, s>>>(P, gx, gy, radii, g.rec, g.tiles_touched, tile_mask, im, bn, cap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_tile_sort<<<gx * gy, SORT_THREADS, 0, s>>>(im, bn, cap);

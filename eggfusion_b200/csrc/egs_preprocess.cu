@@ -40,9 +40,13 @@ __global__ void __launch_bounds__(SURF_THREADS)
 k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
                  const float* __restrict__ colors, const int32_t* __restrict__ tile_mask, GeomView g, ImgView im,
-                 int32_t* __restrict__ radii, uint8_t* __restrict__ active) {
+                 int32_t* __restrict__ radii, uint8_t* __restrict__ active, int own_first, int own_count) {
+    // own_first / own_count: the surfel range this rank owns in a tile-sharded frame.  A visible surfel whose
+    // rectangle has no tile in the rank's mask and which lies outside the range is needed by nobody here: its colour
+    // (SH evaluation, 192 B of coefficients) and its record / cov3D / clamp state are skipped.  SH_SMEM == 3 is the
+    // staging for that case: the row's bulk copy is issued only once the thread knows it needs it.
     __shared__ FrameConst fc;
-    __shared__ __align__(128) float s_sh[SH_SMEM == 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
+    __shared__ __align__(128) float s_sh[SH_SMEM >= 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
     __shared__ __align__(8) unsigned long long s_bar;
     load_frame_const(fc, f);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,8 +55,8 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
         const int row0 = blockIdx.x * SURF_THREADS;
         stage_sh_rows(s_sh, shs + (size_t)48 * row0, min(SURF_THREADS, f.num_surfels - row0));
     }
-    if (SH_SMEM == 2 && threadIdx.x == 0) {
-        mbar_init(bar, 1u);
+    if ((SH_SMEM == 2 || SH_SMEM == 3) && threadIdx.x == 0) {
+        mbar_init(bar, SH_SMEM == 2 ? 1u : (uint32_t)SURF_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -64,51 +68,17 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
             bulk_copy_g2s(smem_addr(s_sh) + 4u * SH_BULK_PITCH * threadIdx.x, shs + (size_t)48 * (row0 + threadIdx.x), 192u, bar);
     }
     const bool valid = i < f.num_surfels;
-    bool visible = false;
+    bool visible = false, need = false;
+    SurfelFwd o;
+    uint32_t cnt = 0;
+    const bool use_sh = colors == nullptr;
+    const float* mean = means + (size_t)3 * (valid ? i : 0);
     if (valid) {
-        SurfelFwd o;
-        const bool use_sh = colors == nullptr;
-        const float* mean = means + (size_t)3 * i;
         surfel_forward(fc, mean, scales + (size_t)3 * i, rots + (size_t)4 * i, __ldg(opac + i), o);
         radii[i] = o.radius;
         active[i] = (uint8_t)o.active;
-        uint32_t cnt = 0;
         if (o.radius > 0) {
             visible = true;
-            if (SH_SMEM == 2) {
-                mbar_wait(bar, 0u);
-                surfel_color(fc, mean, s_sh + threadIdx.x * SH_BULK_PITCH, true, o);
-            } else if (SH_SMEM == 1) {
-                surfel_color(fc, mean, s_sh + threadIdx.x * SH_PITCH, true, o);
-            } else if (use_sh) {
-                // generic layout: this surfel's 3*(D+1)^2 floats into registers (16-byte vectors when rows allow it)
-                float shreg[48];
-                const float* src = shs + (size_t)3 * fc.M * i;
-                const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
-                if (((3 * fc.M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
-#pragma unroll
-                    for (int q = 0; q < 12; q++)
-                        if (4 * q < nfl) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
-                            shreg[4 * q] = v.x; shreg[4 * q + 1] = v.y; shreg[4 * q + 2] = v.z; shreg[4 * q + 3] = v.w;
-                        }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 48; k++)
-                        if (k < nfl) shreg[k] = __ldg(src + k);
-                }
-                surfel_color(fc, mean, shreg, true, o);
-            } else {
-                surfel_color(fc, mean, colors + (size_t)3 * i, false, o);
-            }
-            float4* dst = reinterpret_cast<float4*>(g.rec + i);
-            const float4* src = reinterpret_cast<const float4*>(&o.rec);
-            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-            float2* c2 = reinterpret_cast<float2*>(g.cov3D + (size_t)6 * i);
-            c2[0] = make_float2(o.cov3D[0], o.cov3D[1]);
-            c2[1] = make_float2(o.cov3D[2], o.cov3D[3]);
-            c2[2] = make_float2(o.cov3D[4], o.cov3D[5]);
-            g.clamped[i] = (uint8_t)o.clamped;
             // per-tile instance counts: the histogram that replaces the reference's per-surfel scan
             for (int y = o.y0; y < o.y1; y++)
                 for (int x = o.x0; x < o.x1; x++) {
@@ -118,12 +88,58 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
                         cnt++;
                     }
                 }
+            need = cnt > 0u || (i >= own_first && i - own_first < own_count);
         }
         g.tiles_touched[i] = cnt;
     }
+    if (SH_SMEM == 3) {
+        // every thread arrives exactly once, before anybody waits: the ones that need their SH row add its bytes
+        if (need) {
+            mbar_expect_tx(bar, 192u);
+            bulk_copy_g2s(smem_addr(s_sh) + 4u * SH_BULK_PITCH * threadIdx.x, shs + (size_t)48 * i, 192u, bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    }
+    if (need) {
+        if (SH_SMEM >= 2) {
+            mbar_wait(bar, 0u);
+            surfel_color(fc, mean, s_sh + threadIdx.x * SH_BULK_PITCH, true, o);
+        } else if (SH_SMEM == 1) {
+            surfel_color(fc, mean, s_sh + threadIdx.x * SH_PITCH, true, o);
+        } else if (use_sh) {
+            // generic layout: this surfel's 3*(D+1)^2 floats into registers (16-byte vectors when rows allow it)
+            float shreg[48];
+            const float* src = shs + (size_t)3 * fc.M * i;
+            const int nfl = 3 * (fc.D + 1) * (fc.D + 1);
+            if (((3 * fc.M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 12; q++)
+                    if (4 * q < nfl) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+                        shreg[4 * q] = v.x; shreg[4 * q + 1] = v.y; shreg[4 * q + 2] = v.z; shreg[4 * q + 3] = v.w;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 48; k++)
+                    if (k < nfl) shreg[k] = __ldg(src + k);
+            }
+            surfel_color(fc, mean, shreg, true, o);
+        } else {
+            surfel_color(fc, mean, colors + (size_t)3 * i, false, o);
+        }
+        float4* dst = reinterpret_cast<float4*>(g.rec + i);
+        const float4* src = reinterpret_cast<const float4*>(&o.rec);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        float2* c2 = reinterpret_cast<float2*>(g.cov3D + (size_t)6 * i);
+        c2[0] = make_float2(o.cov3D[0], o.cov3D[1]);
+        c2[1] = make_float2(o.cov3D[2], o.cov3D[3]);
+        c2[2] = make_float2(o.cov3D[4], o.cov3D[5]);
+        g.clamped[i] = (uint8_t)o.clamped;
+    }
     const unsigned ballot = __ballot_sync(0xffffffffu, visible);
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&im.counters->num_visible, __popc(ballot));
-    if (SH_SMEM == 2) mbar_wait(bar, 0u);   // the CTA must not retire while bulk copies into its shared memory are in flight
+    if (SH_SMEM >= 2) mbar_wait(bar, 0u);   // the CTA must not retire while bulk copies into its shared memory are in flight
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -295,7 +311,8 @@ k_mark_visible(int P, const float* __restrict__ means, const float* __restrict__
 // ------------------------------------------------------------------------------------------------ launchers
 cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const float* scales, const float* rots,
                                   const float* opac, const float* shs, const float* colors, const int32_t* tile_mask,
-                                  GeomView g, ImgView im, int32_t* radii, uint8_t* active, cudaStream_t s) {
+                                  GeomView g, ImgView im, int32_t* radii, uint8_t* active, int own_first, int own_count,
+                                  cudaStream_t s) {
     const int P = f.num_surfels;
     if (P == 0) return cudaSuccess;
     // staged-SH fast path: SH colours with exactly 16 coefficients per surfel and 16-byte aligned rows
@@ -307,15 +324,19 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
         const char* e = getenv("EGS_SH_STAGE");
         sh_bulk = (e && e[0] == 'l') ? 0 : 1;
     }
-    if (sh_smem && sh_bulk)
+    const bool sharded = tile_mask != nullptr && own_count < P;   // most SH rows will not be needed: fetch on demand
+    if (sh_smem && sharded)
+        k_surfel_forward<3><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
+                                                            radii, active, own_first, own_count);
+    else if (sh_smem && sh_bulk)
         k_surfel_forward<2><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
-                                                            radii, active);
+                                                            radii, active, own_first, own_count);
     else if (sh_smem)
         k_surfel_forward<1><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
-                                                            radii, active);
+                                                            radii, active, own_first, own_count);
     else
         k_surfel_forward<0><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
-                                                                im, radii, active);
+                                                                im, radii, active, own_first, own_count);
     return cudaGetLastError();
 }
 

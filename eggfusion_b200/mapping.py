@@ -67,8 +67,10 @@ def _mask_u8(m: Optional[torch.Tensor], what: str):
 
 
 def loss_seed(est_color, est_depth, est_normal, ref_color, ref_depth, ref_normal, rgb_mask, geo_mask,
-              weights: MappingWeights, out=None):
-    """egm_loss_seed on caller tensors.  Returns (terms[8] float64, dL_dcolor, dL_ddepth, dL_dnormal)."""
+              weights: MappingWeights, out=None, tile_mask=None):
+    """egm_loss_seed on caller tensors.  Returns (terms[8] float64, dL_dcolor, dL_ddepth, dL_dnormal).
+    `tile_mask` (int32 [tiles_y, tiles_x], a rank's share of a tile-sharded frame): sums and seeds only over the pixels
+    of those tiles, the means' denominator stays the whole frame's (egm_loss_seed_tiles)."""
     lib = _lib.load()
     est_color, est_depth, est_normal = (_cuda_f32(est_color, "est_color"), _cuda_f32(est_depth, "est_depth"),
                                         _cuda_f32(est_normal, "est_normal"))
@@ -85,11 +87,12 @@ def loss_seed(est_color, est_depth, est_normal, ref_color, ref_depth, ref_normal
                torch.empty_like(est_depth), torch.empty_like(est_normal))
     terms, gc, gd, gn = out
     with torch.cuda.device(dev):
-        _lib.check(lib.egm_loss_seed(H, W, est_color.data_ptr(), est_depth.data_ptr(), est_normal.data_ptr(),
-                                     ref_color.data_ptr(), R._ptr(ref_depth), R._ptr(ref_normal), rm.data_ptr(),
-                                     None if gm is None else gm.data_ptr(), weights.color_weight, weights.depth_weight,
-                                     weights.normal_weight, gc.data_ptr(), gd.data_ptr(), gn.data_ptr(),
-                                     terms.data_ptr(), R._stream_ptr(dev)), "loss_seed")
+        _lib.check(lib.egm_loss_seed_tiles(H, W, est_color.data_ptr(), est_depth.data_ptr(), est_normal.data_ptr(),
+                                           ref_color.data_ptr(), R._ptr(ref_depth), R._ptr(ref_normal), rm.data_ptr(),
+                                           None if gm is None else gm.data_ptr(), R._ptr(tile_mask),
+                                           weights.color_weight, weights.depth_weight, weights.normal_weight,
+                                           gc.data_ptr(), gd.data_ptr(), gn.data_ptr(), terms.data_ptr(),
+                                           R._stream_ptr(dev)), "loss_seed")
     return terms, gc, gd, gn
 
 
@@ -199,9 +202,12 @@ class FrameBatchOptimizer:
                               lr.feature_lr / 20.0, lr.opacity_lr, lr.scaling_lr, lr.rotation_lr, self.step_count,
                               w.reg_weight, w.reg_weight_n)
 
-    def step(self, grads=None) -> None:
+    def step(self, grads=None, first: int = 0, count: Optional[int] = None) -> None:
         """optimizer.step() + optimizer.zero_grad(): `grads` = dict xyz, shs, opacity, scales, rotations of gradients
-        w.r.t. the activated parameters (default: the .grad of `total_params`)."""
+        w.r.t. the activated parameters (default: the .grad of `total_params`).
+        `first`, `count`: update only the surfel rows [first, first + count) (a rank's owned range in a sharded
+        optimisation, parallel.DistributedMapper); the regulariser's partial sums in `self.reg` then cover that range
+        only and the caller adds the ranks' parts."""
         if grads is None:
             tp = self.total_params
             zero = lambda t: torch.zeros_like(t)
@@ -211,16 +217,22 @@ class FrameBatchOptimizer:
         h = self._hyper()
         st = self.state
         dev = self.device
+        count = self.P - first if count is None else int(count)
+        if count < self.P and count > 0:
+            # the kernel averages the normal regulariser over the rows it is given: keep the mean over all P surfels
+            h.reg_weight_n = h.reg_weight_n * (count / self.P)
+        M3 = self.M * 3
+        at = lambda t, width: t.data_ptr() + 4 * width * first      # row `first` of a [P, width] fp32 array
         with torch.cuda.device(dev), torch.no_grad():
             _lib.check(self.lib.egm_adam_step(
-                self.P, self.M, C.byref(h), self.xyz.data_ptr(), self.shs.data_ptr(), self.opacity_raw.data_ptr(),
-                self.scaling_raw.data_ptr(), self.rotation_raw.data_ptr(), g["xyz"].data_ptr(), g["shs"].data_ptr(),
-                g["opacity"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(),
-                st["xyz"][0].data_ptr(), st["xyz"][1].data_ptr(), st["shs"][0].data_ptr(), st["shs"][1].data_ptr(),
-                st["opacity"][0].data_ptr(), st["opacity"][1].data_ptr(), st["scaling"][0].data_ptr(),
-                st["scaling"][1].data_ptr(), st["rotation"][0].data_ptr(), st["rotation"][1].data_ptr(),
-                self.pos0.data_ptr(), self.normal0.data_ptr(), self.reg.data_ptr(), self.opacity.data_ptr(),
-                self.scales.data_ptr(), self.rotations.data_ptr(), R._stream_ptr(dev)), "adam_step")
+                count, self.M, C.byref(h), at(self.xyz, 3), at(self.shs, M3), at(self.opacity_raw, 1),
+                at(self.scaling_raw, 3), at(self.rotation_raw, 4), at(g["xyz"], 3), at(g["shs"], M3),
+                at(g["opacity"], 1), at(g["scales"], 3), at(g["rotations"], 4),
+                at(st["xyz"][0], 3), at(st["xyz"][1], 3), at(st["shs"][0], M3), at(st["shs"][1], M3),
+                at(st["opacity"][0], 1), at(st["opacity"][1], 1), at(st["scaling"][0], 3),
+                at(st["scaling"][1], 3), at(st["rotation"][0], 4), at(st["rotation"][1], 4),
+                at(self.pos0, 3), at(self.normal0, 3), self.reg.data_ptr(), at(self.opacity, 1),
+                at(self.scales, 3), at(self.rotations, 4), R._stream_ptr(dev)), "adam_step")
         if self._leaves is not None:
             for t in self._leaves.values():
                 t.grad = None

@@ -22,7 +22,9 @@ class SplatContext:
     STAGES = ("plan", "render", "bwd_zero", "bwd_render", "bwd_surfels")
 
     def __init__(self, P: int, width: int, height: int, sh_coeffs: int, capacity: int, device="cuda:0",
-                 padded_rows: Optional[int] = None):
+                 padded_rows: Optional[int] = None, own_range=None):
+        """own_range = (first, count): this context is one rank of a tile-sharded frame that owns those surfel rows
+        (egs_forward_plan_sharded skips the colour / record work for surfels nobody on this rank reads)."""
         self.lib = _lib.load()
         self.P, self.W, self.H, self.M, self.cap = int(P), int(width), int(height), int(sh_coeffs), int(capacity)
         self.device = torch.device(device)
@@ -47,6 +49,7 @@ class SplatContext:
             self.counters_host = torch.zeros((4,), dtype=torch.int32).pin_memory()
         self.frame = None
         self._keep = None
+        self.own_range = (0, self.P) if own_range is None else (int(own_range[0]), int(own_range[1]))
 
     def set_camera(self, settings) -> None:
         self.frame, self._keep = R.make_frame(self.P, settings, self.M, self.device)
@@ -57,31 +60,38 @@ class SplatContext:
         lib, fr = self.lib, self.frame
         stream = R._stream_ptr(self.device)
         tm = None if tile_mask is None else tile_mask.data_ptr()
-        _lib.check(lib.egs_forward_plan(C.byref(fr), means3D.data_ptr(), R._ptr(shs), R._ptr(colors_precomp),
-                                        opacities.data_ptr(), scales.data_ptr(), rotations.data_ptr(), tm,
-                                        self.geom.data_ptr(), self.img.data_ptr(), self.radii.data_ptr(),
-                                        self.active.data_ptr(), None, stream), "forward_plan")
+        with torch.cuda.device(self.device):
+            _lib.check(lib.egs_forward_plan_sharded(C.byref(fr), means3D.data_ptr(), R._ptr(shs), R._ptr(colors_precomp),
+                                                    opacities.data_ptr(), scales.data_ptr(), rotations.data_ptr(), tm,
+                                                    self.own_range[0], self.own_range[1], self.geom.data_ptr(),
+                                                    self.img.data_ptr(), self.radii.data_ptr(), self.active.data_ptr(),
+                                                    None, stream), "forward_plan")
         if mark:
             mark("plan")
-        _lib.check(lib.egs_forward_render(C.byref(fr), tm, self.radii.data_ptr(), self.geom.data_ptr(),
-                                          self.img.data_ptr(), self.bin.data_ptr(), self.cap, self.color.data_ptr(),
-                                          self.normal.data_ptr(), self.depth.data_ptr(), self.opacity.data_ptr(),
-                                          self.counters_host.data_ptr() if fetch_counters else None,
-                                          0 if save else _lib.EGS_FWD_NO_SAVE, stream),
-                   "forward_render")
+        with torch.cuda.device(self.device):
+            _lib.check(lib.egs_forward_render(C.byref(fr), tm, self.radii.data_ptr(), self.geom.data_ptr(),
+                                              self.img.data_ptr(), self.bin.data_ptr(), self.cap, self.color.data_ptr(),
+                                              self.normal.data_ptr(), self.depth.data_ptr(), self.opacity.data_ptr(),
+                                              self.counters_host.data_ptr() if fetch_counters else None,
+                                              0 if save else _lib.EGS_FWD_NO_SAVE, stream),
+                       "forward_render")
         if mark:
             mark("render")
 
-    def backward_render(self, g_color, g_normal, g_depth, g_opac, mark=None) -> None:
+    def backward_render(self, g_color, g_normal, g_depth, g_opac, mark=None, prezeroed: bool = False) -> None:
+        """prezeroed: the screen-gradient block is known to be all zeros already (the peer exchange of a sharded step
+        clears every row it pushes, parallel.PeerExchange), so the 64 B/surfel memset is skipped."""
         lib, fr = self.lib, self.frame
         stream = R._stream_ptr(self.device)
-        self.screen[:self.P].zero_()
-        if mark:
-            mark("bwd_zero")
-        _lib.check(lib.egs_backward_render(C.byref(fr), self.geom.data_ptr(), self.img.data_ptr(),
-                                           self.bin.data_ptr(), self.cap, g_color.data_ptr(), g_normal.data_ptr(),
-                                           g_depth.data_ptr(), g_opac.data_ptr(), self.screen.data_ptr(),
-                                           _lib.EGS_BWD_GRADS_PREZEROED, stream), "backward_render")
+        with torch.cuda.device(self.device):
+            if not prezeroed:
+                self.screen[:self.P].zero_()
+            if mark:
+                mark("bwd_zero")
+            _lib.check(lib.egs_backward_render(C.byref(fr), self.geom.data_ptr(), self.img.data_ptr(),
+                                               self.bin.data_ptr(), self.cap, g_color.data_ptr(), g_normal.data_ptr(),
+                                               g_depth.data_ptr(), g_opac.data_ptr(), self.screen.data_ptr(),
+                                               _lib.EGS_BWD_GRADS_PREZEROED, stream), "backward_render")
         if mark:
             mark("bwd_render")
 
@@ -91,15 +101,16 @@ class SplatContext:
         stream = R._stream_ptr(self.device)
         count = self.P - first if count is None else count
         use_sh = shs is not None
-        _lib.check(lib.egs_backward_surfels(C.byref(fr), first, count, means3D.data_ptr(), R._ptr(shs),
-                                            R._ptr(colors_precomp), scales.data_ptr(), rotations.data_ptr(),
-                                            self.radii.data_ptr(), self.geom.data_ptr(),
-                                            self.screen.data_ptr() if screen_base is None else screen_base,
-                                            self.d_means.data_ptr(), self.d_opac.data_ptr(),
-                                            self.d_sh.data_ptr() if use_sh else None, self.d_scales.data_ptr(),
-                                            self.d_rots.data_ptr(), None,
-                                            None if use_sh else self.d_colors.data_ptr(), None, stream),
-                   "backward_surfels")
+        with torch.cuda.device(self.device):
+            _lib.check(lib.egs_backward_surfels(C.byref(fr), first, count, means3D.data_ptr(), R._ptr(shs),
+                                                R._ptr(colors_precomp), scales.data_ptr(), rotations.data_ptr(),
+                                                self.radii.data_ptr(), self.geom.data_ptr(),
+                                                self.screen.data_ptr() if screen_base is None else screen_base,
+                                                self.d_means.data_ptr(), self.d_opac.data_ptr(),
+                                                self.d_sh.data_ptr() if use_sh else None, self.d_scales.data_ptr(),
+                                                self.d_rots.data_ptr(), None,
+                                                None if use_sh else self.d_colors.data_ptr(), None, stream),
+                       "backward_surfels")
         if mark:
             mark("bwd_surfels")
 

@@ -185,10 +185,12 @@ def _bin_bytes_forward_only(cap: int) -> int:
 
 
 def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotations, tile_mask, capacity=None,
-                save=True):
+                save=True, own_range=None):
     """Run the CUDA forward.  Returns (color, normal, depth, opacity, active_mask, radii, ForwardState).
     save=False: forward-only render (EGS_FWD_NO_SAVE): nothing is kept for a backward, the binning workspace is 12
-    instead of 76 bytes per instance."""
+    instead of 76 bytes per instance.
+    own_range=(first, count): one rank of a tile-sharded frame (parallel.py): colour / record work is skipped for
+    surfels that touch none of `tile_mask`'s tiles and lie outside the owned rows (egs_forward_plan_sharded)."""
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:60-62
@@ -245,11 +247,12 @@ def forward_raw(settings, means3D, shs, colors_precomp, opacities, scales, rotat
                 "possible inside a graph): set eggfusion_b200.rasterizer.config.capacity to an int, or to 'auto' and "
                 "run one eager forward of this shape first")
         host = None if capturing else _get_pinned()
-        _lib.check(lib.egs_forward_plan(C.byref(frame), _ptr(means3D), _ptr(shs) if use_sh else None,
-                                        None if use_sh else _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
-                                        _ptr(rotations), _ptr(tile_mask), st.geom.data_ptr(), st.img.data_ptr(),
-                                        _ptr(radii), _ptr(active), host.data_ptr() if exact else None, stream),
-                   "forward_plan")
+        own_first, own_count = (0, P) if own_range is None else (int(own_range[0]), int(own_range[1]))
+        _lib.check(lib.egs_forward_plan_sharded(C.byref(frame), _ptr(means3D), _ptr(shs) if use_sh else None,
+                                                None if use_sh else _ptr(colors_precomp), _ptr(opacities), _ptr(scales),
+                                                _ptr(rotations), _ptr(tile_mask), own_first, own_count,
+                                                st.geom.data_ptr(), st.img.data_ptr(), _ptr(radii), _ptr(active),
+                                                host.data_ptr() if exact else None, stream), "forward_plan")
         if exact:
             torch.cuda.current_stream(device).synchronize()
             st.num_rendered, st.tile_num = int(host[0]), int(host[1])

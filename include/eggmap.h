@@ -66,6 +66,16 @@ EGS_API int egm_loss_seed(int32_t height, int32_t width, const float* est_color,
                           float color_weight, float depth_weight, float normal_weight, float* dL_dcolor,
                           float* dL_ddepth, float* dL_dnormal, double* terms, void* stream);
 
+/* egm_loss_seed for one rank of a tile-sharded frame: `tile_mask` ([tiles_y][tiles_x] int32, the mask the
+ * rank renders with; NULL = all tiles) restricts the partial sums and the seeds to the pixels of the rank's tiles, while
+ * the means' denominator stays the number of masked pixels of the WHOLE frame -- so the ranks' terms[1..4] add up
+ * (all-reduce) to the single-GPU values and their seeds are the single-GPU seeds on disjoint pixel sets. */
+EGS_API int egm_loss_seed_tiles(int32_t height, int32_t width, const float* est_color, const float* est_depth,
+                                const float* est_normal, const float* ref_color, const float* ref_depth,
+                                const float* ref_normal, const uint8_t* rgb_mask, const uint8_t* geo_mask,
+                                const int32_t* tile_mask, float color_weight, float depth_weight, float normal_weight,
+                                float* dL_dcolor, float* dL_ddepth, float* dL_dnormal, double* terms, void* stream);
+
 /* One fused optimiser step over P surfels with sh_coeffs SH coefficients.
  * raw parameters (updated in place): xyz[P,3], shs[P,M,3] (row 0 = _features_dc, rows 1.. = _features_rest; identity
  * activation), opacity_raw[P,1] (logit), scaling_raw[P,3] (log), rotation_raw[P,4].

@@ -109,6 +109,32 @@ EGS_API int egs_forward_plan(const egs_frame* frame, const float* means3D, const
                      void* stream);
 
 /*
+ * egs_forward_plan for one rank of a tile-sharded frame (the seam is the reference's tile_mask,
+ * forward.cu:292-300, rasterizer_impl.cu:103-111).  The rank renders the tiles of `tile_mask` and owns the surfels
+ * [own_first, own_first + own_count) for the per-surfel backward.  radii / active_mask / tiles_touched are written for
+ * every surfel as usual, but the colour (SH evaluation), the splat record and the per-surfel backward state of a
+ * visible surfel are produced only if it touches one of the rank's tiles or lies in the owned range -- nobody on this
+ * rank reads them otherwise.  egs_forward_plan == own range [0, P).
+ */
+EGS_API int egs_forward_plan_sharded(const egs_frame* frame, const float* means3D, const float* shs,
+                                     const float* colors_precomp, const float* opacities, const float* scales,
+                                     const float* rotations, const int32_t* tile_mask, int32_t own_first,
+                                     int32_t own_count, void* geom, void* img, int32_t* radii, uint8_t* active_mask,
+                                     egs_counters* counters_host, void* stream);
+
+/*
+ * Exchange step of a tile-sharded frame over peer memory (one process per GPU, NVLink / NVSwitch): adds the rows of
+ * `local_screen_grads` [P][16] that this rank's reverse walk touched to their owners' accumulation blocks and clears
+ * them locally.  peer_blocks: DEVICE array of world_size pointers, peer_blocks[r] = rank r's block of `chunk_rows` rows
+ * for surfels [r * chunk_rows, (r+1) * chunk_rows) (peer-mapped addresses; r == own rank: the local block).  The
+ * caller orders it against the owners' readers (a barrier after this call on every rank).  Replaces a dense NCCL
+ * reduce-scatter of the whole block: only touched rows cross the links, as 16-byte reductions performed by the
+ * owner's L2.
+ */
+EGS_API int egs_push_rows(int32_t num_surfels, int32_t chunk_rows, const void* geom, float* local_screen_grads,
+                          float* const* peer_blocks, void* stream);
+
+/*
  * Instance emission, per-tile depth sort and front-to-back compositing.  `bin` must hold `cap_instances`
  * instances (see egs_workspace_sizes); if the true count is larger the lists are truncated and
  * counters.overflow is set.  All four images are fully written (tiles without surfels get zeros, like the

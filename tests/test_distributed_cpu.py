@@ -91,3 +91,47 @@ def test_reduce_scatter_rows_gloo_world2(P):
         assert first == r * chunk or count == 0
         covered += count
     assert covered == P
+
+
+def _gather_worker(rank, world, port, P, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunk = par.padded_rows(P, world) // world
+        first, count = par.surfel_range(P, world, rank)
+        # every rank starts from the same replica and "updates" only its owned rows
+        t = torch.arange(P * 3, dtype=torch.float32).view(P, 3).clone()
+        t[first:first + count] += 1000.0 * (rank + 1)
+        par.all_gather_rows(t, first, count, chunk, world)
+        out[rank] = t.clone()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [7, 1000])
+def test_all_gather_rows_gloo_world2(P):
+    """The second half of SURVEY 8e: after the owners updated their rows, one all-gather makes every replica whole."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, port, P, out), nprocs=world, join=True)
+    want = torch.arange(P * 3, dtype=torch.float32).view(P, 3).clone()
+    for r in range(world):
+        first, count = par.surfel_range(P, world, r)
+        want[first:first + count] += 1000.0 * (r + 1)
+    for r in range(world):
+        assert torch.equal(out[r], want)
+
+
+def test_sharded_api_surface():
+    """The autograd-level sharded rasterizer mirrors GaussianRasterizer's argument checks; the exchange falls back to
+    NCCL / gloo collectives when peer memory is unavailable (here: no process group at all -> world 1)."""
+    sh = par.ShardedSplat()
+    assert sh.world == 1 and sh.rank == 0
+    assert par.make_exchange(100, "cpu") is None
+    r = par.ShardedRasterizer(raster_settings=None, sharder=sh)
+    with pytest.raises(Exception, match="excatly one"):
+        r(means3D=torch.zeros(1, 3), opacities=torch.zeros(1, 1))
+    assert r.owned_range(10) == (0, 10)
