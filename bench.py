@@ -491,105 +491,137 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E.load()
-    scene, cams, grads, deg = make_workload(args.workload)
-    P, M = scene["xyz"].shape[0], scene["shs"].shape[1]
-    W, H = cams[0].width, cams[0].height
-    N_px = W * H
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    params = {k: t(scene[k]) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
-    bg = t(np.zeros(3, np.float32))
-    settings = [E.GaussianRasterizationSettings(
-        image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
-        viewmatrix=t(c.viewmatrix), projmatrix=t(c.projmatrix), sh_degree=deg, campos=t(c.campos), prefiltered=False,
-        debug=False, cx=c.cx, cy=c.cy) for c in cams]
-    pix = [tuple(t(g[k]) for k in ("color", "normal", "depth", "opacity")) for g in grads]
-    ty, tx = cams[0].tiles
-    mask = par.tile_partition(ty, tx, world, rank).to(dev) if world > 1 else None
     empty = torch.Tensor([])
-
-    # instance counts per camera (exact mode, outside the timed region) -> capacity of the persistent context
-    I_cam, vis_cam = [], []
-    for s in settings:
-        out = R.forward_raw(s, params["xyz"], params["shs"], empty, params["opacity"], params["scales"],
-                            params["rotations"], mask)
-        I_cam.append(out[6].num_rendered)
-        vis_cam.append(int((out[5] > 0).sum()))
-        del out
-    cap = int(max(I_cam) * 1.05) + 4096
-    Pp = par.padded_rows(P, world)
-    ctx = SplatContext(P, W, H, M, cap, device=dev, padded_rows=Pp)
-    first, count = par.surfel_range(P, world, rank)
-    chunk = Pp // world
-
-    stage_ev = {}
-
-    def one_step(i, timed):
-        ci = i % len(settings)
-        ctx.set_camera(settings[ci])
-        marks = []
-
-        def mark(name):
-            if timed:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((name, e))
-        if timed:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            marks.append(("start", e0))
-        ctx.forward(params["xyz"], params["shs"], None, params["opacity"], params["scales"], params["rotations"],
-                    mask, mark)
-        ctx.backward_render(*pix[ci], mark=mark)
-        if world > 1:
-            mine = par.reduce_scatter_rows(ctx.screen, None)
-            mark("reduce_scatter")
-            base = mine.data_ptr() - rank * chunk * 64
-            ctx.backward_surfels(params["xyz"], params["shs"], None, params["scales"], params["rotations"], first,
-                                 count, screen_base=base, mark=mark)
-        else:
-            ctx.backward_surfels(params["xyz"], params["shs"], None, params["scales"], params["rotations"],
-                                 mark=mark)
-        if timed:
-            stage_ev[i] = marks
-        return ci
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
-        one_step(i, False)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    used = [one_step(i, True) for i in range(args.steps)]
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    counters = ctx.read_counters()
-    assert counters[2] == 0, "binning capacity overflow inside the timed region"
+    def device_resident(workload):
+        """The `value` leg on one workload: forward + backward with inputs resident in HBM, persistent workspaces, no
+        host round trip in the timed region.  N > 1: tile-sharded (cost-balanced tile rows), exchange of the touched
+        screen-gradient rows over NVLink peer memory (NCCL reduce-scatter if unavailable), per-surfel backward on the
+        owned surfel range."""
+        scene, cams, grads, deg = make_workload(workload)
+        P, M = scene["xyz"].shape[0], scene["shs"].shape[1]
+        W, H = cams[0].width, cams[0].height
+        params = {k: t(scene[k]) for k in ("xyz", "opacity", "shs", "scales", "rotations")}
+        bg = t(np.zeros(3, np.float32))
+        settings = [E.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
+            viewmatrix=t(c.viewmatrix), projmatrix=t(c.projmatrix), sh_degree=deg, campos=t(c.campos), prefiltered=False,
+            debug=False, cx=c.cx, cy=c.cy) for c in cams]
+        pix = [tuple(t(g[k]) for k in ("color", "normal", "depth", "opacity")) for g in grads]
+        ty, tx = cams[0].tiles
+        mask, costs = None, None
+        if world > 1:
+            # per-tile list lengths of the previous frames (here: the workload's cameras, outside the timed region)
+            costs = torch.zeros((ty * tx,), dtype=torch.float64, device=dev)
+            for s in settings:
+                out = R.forward_raw(s, params["xyz"], params["shs"], empty, params["opacity"], params["scales"],
+                                    params["rotations"], None)
+                rg = R.debug_export(out[6], P, W, H)["ranges"].double()
+                costs += rg[:, 1] - rg[:, 0]
+                del out, rg
+            mask = par.tile_partition(ty, tx, world, rank, None if args.round_robin else costs).to(dev)
+        # instance counts per camera (exact mode, outside the timed region) -> capacity of the persistent context
+        I_cam, vis_cam = [], []
+        for s in settings:
+            out = R.forward_raw(s, params["xyz"], params["shs"], empty, params["opacity"], params["scales"],
+                                params["rotations"], mask)
+            I_cam.append(out[6].num_rendered)
+            vis_cam.append(int((out[5] > 0).sum()))
+            del out
+        cap = int(max(I_cam) * 1.05) + 4096
+        Pp = par.padded_rows(P, world)
+        first, count = par.surfel_range(P, world, rank)
+        chunk = Pp // world
+        ctx = SplatContext(P, W, H, M, cap, device=dev, padded_rows=Pp,
+                           own_range=(first, count) if world > 1 else None)
+        exch = par.make_exchange(P, dev) if world > 1 else None
+        stage_ev = {}
 
-    # per-stage means over the timed steps
-    stage_ms = {}
-    for marks in stage_ev.values():
-        for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
-            stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
-    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+        def one_step(i, timed):
+            ci = i % len(settings)
+            ctx.set_camera(settings[ci])
+            marks = []
 
-    I_mean = float(np.mean([I_cam[c] for c in used]))
-    vis_mean = float(np.mean([vis_cam[c] for c in used]))
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    Isum = torch.tensor([I_mean], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(Isum, op=dist.ReduceOp.SUM)
-    ms_step = float(tmax.item()) / args.steps
-    I_total = float(Isum.item())
-    value = 256.0 * I_total / (ms_step * 1e-3) / 1e6
+            def mark(name):
+                if timed:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    marks.append((name, e))
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                marks.append(("start", e0))
+            ctx.forward(params["xyz"], params["shs"], None, params["opacity"], params["scales"], params["rotations"],
+                        mask, mark)
+            ctx.backward_render(*pix[ci], mark=mark, prezeroed=exch is not None)
+            if world > 1:
+                if exch is not None:
+                    base = exch.exchange(ctx.geom, ctx.screen, R._stream_ptr(dev), mark)
+                else:
+                    mine = par.reduce_scatter_rows(ctx.screen, None)
+                    mark("reduce_scatter")
+                    base = mine.data_ptr() - rank * chunk * 64
+                ctx.backward_surfels(params["xyz"], params["shs"], None, params["scales"], params["rotations"], first,
+                                     count, screen_base=base, mark=mark)
+                if exch is not None:
+                    exch.consumed()
+            else:
+                ctx.backward_surfels(params["xyz"], params["shs"], None, params["scales"], params["rotations"],
+                                     mark=mark)
+            if timed:
+                stage_ev[i] = marks
+            return ci
+
+        for i in range(args.warmup):
+            one_step(i, False)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        used = [one_step(i, True) for i in range(args.steps)]
+        ev1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms_total = ev0.elapsed_time(ev1)
+        counters = ctx.read_counters()
+        assert counters[2] == 0, "binning capacity overflow inside the timed region"
+        # per-stage means over the timed steps
+        stage_ms = {}
+        for marks in stage_ev.values():
+            for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
+                stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
+        stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+        I_mean = float(np.mean([I_cam[c] for c in used]))
+        vis_mean = float(np.mean([vis_cam[c] for c in used]))
+        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        Isum = torch.tensor([I_mean], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(Isum, op=dist.ReduceOp.SUM)
+        ms_step = float(tmax.item()) / args.steps
+        I_total = float(Isum.item())
+        del ctx
+        return dict(scene=scene, cams=cams, grads=grads, deg=deg, P=P, M=M, W=W, H=H, params=params, bg=bg,
+                    settings=settings, mask=mask, costs=costs, cap=cap, stage_ms=stage_ms, I_mean=I_mean,
+                    vis_mean=vis_mean, ms_step=ms_step, I_total=I_total, clocks=clocks, exchange=exch,
+                    value=256.0 * I_total / (ms_step * 1e-3) / 1e6)
+
+    main_run = device_resident(args.workload)
+    exchange_kind = main_run["exchange"] is not None
+    scene, cams, grads, deg = main_run["scene"], main_run["cams"], main_run["grads"], main_run["deg"]
+    P, M, W, H, params, bg = (main_run[k] for k in ("P", "M", "W", "H", "params", "bg"))
+    settings, mask, cap = main_run["settings"], main_run["mask"], main_run["cap"]
+    stage_ms, I_mean, vis_mean = main_run["stage_ms"], main_run["I_mean"], main_run["vis_mean"]
+    ms_step, I_total, value, clocks = main_run["ms_step"], main_run["I_total"], main_run["value"], main_run["clocks"]
+    N_px = W * H
+    ty, tx = cams[0].tiles
 
     # ---- e2e through the public API, host buffers in the timed region (rank-local tiles when sharded)
     e2e, e2e_eager = None, None
@@ -613,14 +645,30 @@ def run_ours(args):
         s_static = E.GaussianRasterizationSettings(H, W, c0.tanfovx, c0.tanfovy, bg, 1.0, st_view, st_proj, deg, st_campos,
                                                    False, False, c0.cx, c0.cy)
 
+        sharder = par.ShardedSplat(costs=None if args.round_robin else main_run["costs"]) if world > 1 else None
+        srast = par.ShardedRasterizer(s_static, sharder) if world > 1 else None
+        px_mask = srast.pixel_mask().float() if world > 1 else None
+        inv_npx = 1.0 / float(H * W)
+
         def api_step():
-            """The call a user makes: the reference-facing rasterizer + a torch loss + loss.backward()."""
-            color, normal, depth, opac, _a, _r = E.GaussianRasterizer(s_static)(
-                means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
-                rotations=leaf["rotations"], tile_mask=mask)
-            loss = (color - st_tc).abs().mean() + (depth - st_td).abs().mean() + 0.1 * (1 - normal[2]).mean()
+            """The call a user makes: the reference-facing rasterizer + a torch loss + loss.backward().  N > 1: the
+            sharded rasterizer (exchange inside backward), the loss summed over the rank's own pixels and all-reduced
+            (4 bytes), so the value read back is the frame's loss on every rank."""
+            if world == 1:
+                color, normal, depth, opac, _a, _r = E.GaussianRasterizer(s_static)(
+                    means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"], scales=leaf["scales"],
+                    rotations=leaf["rotations"], tile_mask=mask)
+                loss = (color - st_tc).abs().mean() + (depth - st_td).abs().mean() + 0.1 * (1 - normal[2]).mean()
+                loss.backward()
+                return loss
+            color, normal, depth, opac = srast(means3D=leaf["xyz"], opacities=leaf["opacity"], shs=leaf["shs"],
+                                               scales=leaf["scales"], rotations=leaf["rotations"])
+            loss = ((((color - st_tc).abs().sum(0) * (1.0 / 3.0) + (depth - st_td).abs()[0] + 0.1 * (1 - normal[2]))
+                     * px_mask).sum() * inv_npx)
             loss.backward()
-            return loss
+            total = loss.detach()
+            dist.all_reduce(total)
+            return total
 
         def load_inputs(i):
             for dst, src in zip((st_view, st_proj, st_campos, st_tc, st_td), feeder.get(i)):
@@ -652,8 +700,12 @@ def run_ours(args):
             return {"value": 256.0 * I_total / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
                     "frames_per_s": 1e3 / ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "api": api}
         ms_eager = time_e2e(eager_step)
-        e2e_eager = line_e2e(ms_eager, "eggfusion_b200.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item(), "
-                                       "eager (every call enqueued from Python each step)")
+        e2e_eager = line_e2e(ms_eager, ("eggfusion_b200.GaussianRasterizer" if world == 1 else
+                                        "eggfusion_b200.parallel.ShardedRasterizer (exchange of the screen-gradient rows "
+                                        "inside backward, loss all-reduced)") +
+                             " + torch L1 loss + loss.backward() + loss.item(), eager (every call enqueued from Python each step)")
+        if world > 1:
+            e2e_eager["h2d_bytes_per_step"] = h2d * world   # every rank uploads the frame it takes its tiles from
         e2e = e2e_eager
         if world == 1 and not args.no_graph:
             # The same calls recorded ONCE into a CUDA graph (torch.cuda.graph) and replayed per step: possible because
@@ -691,13 +743,17 @@ def run_ours(args):
             del graph
 
     mapping = None
-    if world == 1 and not args.no_mapping:
+    if not args.no_mapping:
         from eggfusion_b200 import mapping as MP
         R.config.capacity = "exact"
         torch.cuda.empty_cache()
         raw, frames = mapping_inputs(scene, cams, dev)
-        mopt = MP.FrameBatchOptimizer(raw, MP.LrParams(**MAP_LR), MP.MappingWeights(**MAP_WEIGHTS))
-        fm = MP.FusedMapper(mopt, W, H, cap, deg)
+        mopt = MP.FrameBatchOptimizer(raw, MP.LrParams(**MAP_LR), MP.MappingWeights(**MAP_WEIGHTS),
+                                      padded_rows=par.padded_rows(P, world))
+        if world == 1:
+            fm = MP.FusedMapper(mopt, W, H, cap, deg)
+        else:
+            fm = par.DistributedMapper(mopt, W, H, cap, deg, costs=None if args.round_robin else main_run["costs"])
         host_loss = torch.zeros((args.steps + max(3, args.warmup) + 8, 5), dtype=torch.float32).pin_memory()
 
         def map_async(i):
@@ -706,13 +762,21 @@ def run_ours(args):
 
         def map_sync(i):
             return float(fm.iterate(settings[i % len(settings)], *frames[i % len(frames)])[0].item())
+        barrier()
         ms_async = time_loop(map_async, max(3, args.warmup), args.steps)
+        barrier()
         ms_sync = time_loop(map_sync, max(3, args.warmup), args.steps)
         assert fm.ctx.read_counters()[2] == 0, "binning capacity overflow in the mapping loop"
+        if world > 1:
+            tm_ = torch.tensor([ms_async, ms_sync], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm_, op=dist.ReduceOp.MAX)
+            ms_async, ms_sync = float(tm_[0]), float(tm_[1])
         mapping = {"ms_per_iter": ms_async, "iters_per_s": 1e3 / ms_async, "ms_per_iter_loss_item_each_iter": ms_sync,
                    "last_loss": float(host_loss[(max(3, args.warmup) + args.steps - 1) % host_loss.shape[0], 0]),
                    "what": "one Mapper.frame_batch_optimization iteration (activations, render, compute_loss incl. "
-                           "regulariser, backward, Adam over all 6 groups) = eggfusion_b200.mapping.FusedMapper.iterate; "
+                           "regulariser, backward, Adam over all 6 groups) = eggfusion_b200.mapping.FusedMapper.iterate"
+                           + ("" if world == 1 else " sharded over %d GPUs (parallel.DistributedMapper: tile-sharded render, "
+                              "peer exchange, Adam on the owned surfel range, all-gather of the parameters)" % world) + "; "
                            "ms_per_iter: loss copied to pinned host memory asynchronously, "
                            "ms_per_iter_loss_item_each_iter: blocking loss.item() every iteration like the reference loop",
                    "gpu_launches_per_iter": 7 + 2 + 1 + 2}
@@ -733,6 +797,16 @@ def run_ours(args):
                     "what": "dense part of Tracker.tracking_frame: 9 Gauss-Newton steps over a 3-level 1200x680 pyramid "
                             "(eggfusion_b200.tracking.DenseTracker.track: 2 launches per step, no host sync)",
                     "gpu_launches_per_frame": 9 * 3}
+    c4 = None
+    if world > 1 and args.workload == "C3" and not args.no_c4:
+        # BASELINE config 4: 4 M surfels @1080p, tile-sharded over the same N GPUs (device-resident leg only)
+        torch.cuda.empty_cache()
+        r4 = device_resident("C4")
+        c4 = {"workload": config_dict("C4", r4["P"], r4["W"], r4["H"], r4["deg"], r4["M"], r4["I_total"])["workload"],
+              "ms_per_step": r4["ms_step"], "frames_per_s": 1e3 / r4["ms_step"], "value": r4["value"], "unit": UNIT,
+              "instances_per_frame": r4["I_total"], "stage_ms": r4["stage_ms"],
+              "exchange": "nvlink peer memory (egs_push_rows)" if r4["exchange"] is not None else "nccl reduce_scatter"}
+        r4.clear()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -781,12 +855,17 @@ def run_ours(args):
                              "see profiles/README.md",
                      "algorithmic_bytes": dom_bytes, "kernel_ms": stage_ms[dom_stage], "issue_roofline": issue},
         "clocks": clocks,
-        "gpu_launches": 7 * args.steps * world,
+        "gpu_launches": (7 if world == 1 else 10) * args.steps * world,
         "e2e": e2e,
         "e2e_eager": e2e_eager,
         "mapping_iter": mapping,
         "tracking_frame": tracking,
     }
+    if world > 1:
+        line["exchange"] = ("nvlink peer memory (egs_push_rows: the touched rows stored into the owners' inboxes, device "
+                            "barrier, egs_fold_inbox)") if exchange_kind else "nccl reduce_scatter_tensor"
+        line["tile_partition"] = "round-robin tile rows" if args.round_robin else "tile rows balanced by list length"
+        line["c4"] = c4
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)
     print(json.dumps(line))
@@ -954,6 +1033,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--round-robin", action="store_true", help="N > 1: deal tile rows round-robin instead of by cost")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the extra C4 (4 M surfels) line")
     ap.add_argument("--no-graph", action="store_true", help="e2e: eager calls only (no torch.cuda.graph replay)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mapping", action="store_true")

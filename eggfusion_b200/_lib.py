@@ -42,7 +42,8 @@ SIGNATURES = {
     "egs_bin_bytes_forward_only": (C.c_int, [_I64, C.POINTER(C.c_size_t)]),
     "egs_forward_plan": (C.c_int, [C.POINTER(Frame)] + [_P] * 13),
     "egs_forward_plan_sharded": (C.c_int, [C.POINTER(Frame)] + [_P] * 7 + [_I32, _I32] + [_P] * 6),
-    "egs_push_rows": (C.c_int, [_I32, _I32, _P, _P, _P, _P]),
+    "egs_push_rows": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "egs_fold_inbox": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P]),
     "egs_forward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),
     "egs_backward_render": (C.c_int, [C.POINTER(Frame), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I32, _P]),
     "egs_backward_surfels": (C.c_int, [C.POINTER(Frame), _I32, _I32] + [_P] * 17),

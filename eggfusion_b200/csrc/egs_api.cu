@@ -42,24 +42,92 @@ inline int check_frame(const egs_frame* f) {
     } while (0)
 
 // Exchange step of a tile-sharded frame, over NVLink peer memory instead of a dense reduce-scatter.
-// One thread per (surfel, 16-byte quad of its screen-gradient row).  A surfel that touched one of this rank's tiles
-// (tiles_touched != 0; at 8 GPUs ~1/5 of the visible ones) has a partial row in the rank's local block: the thread adds
-// its quad to the OWNER's accumulation block with one red.global.add.v4.f32 on the owner's (peer-mapped) address and
-// clears the local quad, so the local block is all zeros again for the next step (no memset).  Rows nobody touched
-// cost a 4-byte read.  peer_base[r] = rank r's accumulation block for its surfel range [r*chunk, (r+1)*chunk).
+// A surfel that touched one of this rank's tiles (tiles_touched != 0; at 8 GPUs ~1/5 of the visible ones) has a
+// partial row in the rank's local screen-gradient block.  k_push_rows, one CTA per 256 consecutive surfels (all owned
+// by one rank: chunk_rows is a multiple of 256): the touched rows are taken (and cleared, so the local block is all
+// zeros again for the next step: no memset), stamped with their surfel id in the last padding word and compacted
+// into shared memory; ONE counter bump per CTA reserves a run of slots in this sender's section of the OWNER's inbox,
+// and the CTA streams the run there with fully coalesced 16-byte stores on the peer-mapped address (512 contiguous
+// bytes per warp instruction).  k_push_counts publishes the counts; after a barrier the owner folds its inboxes
+// into its (zeroed) block with local reductions (k_fold_inbox).
+// What NVLink wants here was measured (2 x B200, NV18): bulk copy 714 GB/s; 64-byte rows scattered to random peer
+// addresses 94 GB/s; red.global.add.v4.f32 of every quad onto the owner's block 71 GB/s (C3 push stage 0.25 ms);
+// rows stored at their natural (55 % dense) positions 0.20 ms; warp-granular slot counters 0.12 - 0.29 ms (the
+// same-address atomics serialise).  inbox layout on every rank: [world senders][chunk rows][16 floats], header int32 [world].
+#define PUSH_CTA 256
+__global__ void __launch_bounds__(PUSH_CTA)
+k_push_rows(int P, int chunk, int rank, const uint32_t* __restrict__ tiles_touched, float* __restrict__ local_sg,
+            uint32_t* __restrict__ sent, float* const* __restrict__ peer_inbox) {
+    __shared__ __align__(128) float4 s_rows[PUSH_CTA * 4];
+    __shared__ uint32_t s_warp[PUSH_CTA / 32];
+    __shared__ uint32_t s_base;
+    const int i = blockIdx.x * PUSH_CTA + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int owner = (blockIdx.x * PUSH_CTA) / chunk;      // uniform: chunk % PUSH_CTA == 0
+    const bool on = i < P && tiles_touched[i] != 0u;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
+    __syncthreads();
+    uint32_t before = 0u, total = 0u;
+#pragma unroll
+    for (int w = 0; w < PUSH_CTA / 32; w++) {
+        const uint32_t c = s_warp[w];
+        before += w < warp ? c : 0u;
+        total += c;
+    }
+    if (total == 0u) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(sent + owner, total);
+    if (on) {
+        const uint32_t slot = before + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+        float4* src = reinterpret_cast<float4*>(local_sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v0 = src[0], v1 = src[1], v2 = src[2];
+        float4 v3 = src[3];
+        src[0] = z; src[1] = z; src[2] = z; src[3] = z;
+        v3.w = __int_as_float(i);
+        s_rows[4 * slot] = v0; s_rows[4 * slot + 1] = v1; s_rows[4 * slot + 2] = v2; s_rows[4 * slot + 3] = v3;
+    }
+    // the compacted run leaves through the TMA engine: one bulk store of up to 16 KB per CTA on the peer address
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic-proxy writes -> async proxy
+    __syncthreads();
+#ifndef PUSH_NO_TMA
+    if (threadIdx.x == 0) {
+        float* dst = peer_inbox[owner] + ((size_t)rank * chunk + s_base) * EGS_SCREEN_GRAD_STRIDE;
+        bulk_copy_s2g(dst, smem_addr(s_rows), 64u * total);
+        bulk_commit_wait_read();   // the rows must stay in shared memory until the store has read them
+    }
+#else
+    float4* dst = reinterpret_cast<float4*>(peer_inbox[owner] + ((size_t)rank * chunk + s_base) * EGS_SCREEN_GRAD_STRIDE);
+    for (uint32_t k = threadIdx.x; k < 4u * total; k += PUSH_CTA) dst[k] = s_rows[k];
+#endif
+}
+
+__global__ void k_push_counts(int world, int rank, uint32_t* __restrict__ sent, int32_t* const* __restrict__ peer_header) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    peer_header[r][rank] = (int32_t)sent[r];
+    sent[r] = 0u;
+}
+
+// owner side: one thread per (slot, quad) of sender blockIdx.y's section
 __global__ void __launch_bounds__(256)
-k_push_rows(int P, int chunk, const uint32_t* __restrict__ tiles_touched, float* __restrict__ local_sg,
-            float* const* __restrict__ peer_base) {
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int i = (int)(t >> 2), q = (int)(t & 3);
-    if (i >= P || tiles_touched[i] == 0u) return;
-    float4* src = reinterpret_cast<float4*>(local_sg + (size_t)EGS_SCREEN_GRAD_STRIDE * i) + q;
-    const float4 v = *src;
-    *src = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
-    const int owner = i / chunk;
-    float* dst = peer_base[owner] + (size_t)EGS_SCREEN_GRAD_STRIDE * (i - owner * chunk) + 4 * q;
-    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+k_fold_inbox(int chunk, int first, const float* __restrict__ inbox, const int32_t* __restrict__ header,
+             float* __restrict__ block) {
+    const int sender = blockIdx.y;
+    const long long n4 = 4ll * header[sender];
+    const float* sec = inbox + (size_t)sender * chunk * EGS_SCREEN_GRAD_STRIDE;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t >> 2;
+        const int q = (int)(t & 3);
+        const float* src = sec + row * EGS_SCREEN_GRAD_STRIDE;
+        const int id = __float_as_int(__ldg(src + 15));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+        float* dst = block + (size_t)EGS_SCREEN_GRAD_STRIDE * (id - first) + 4 * q;
+        if (q < 3)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        else
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(v.x) : "memory");
+    }
 }
 
 __global__ void k_export_ranges(ImgView im, int tiles, uint32_t* ranges, int32_t* tile_indices) {
@@ -203,15 +271,32 @@ EGS_API int egs_backward_surfels(const egs_frame* f, int32_t first, int32_t coun
     return 0;
 }
 
-EGS_API int egs_push_rows(int32_t P, int32_t chunk_rows, const void* geom, float* local_screen_grads,
-                          float* const* peer_blocks, void* stream) {
-    if (P < 0 || chunk_rows <= 0) return EGS_E_BADARG;
-    if (P == 0) return 0;
-    if (!geom || !local_screen_grads || !peer_blocks) return EGS_E_BADARG;
-    GeomView g = carve_geom(const_cast<void*>(geom), (size_t)P);
-    const long long threads = 4ll * P;
-    k_push_rows<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, chunk_rows, g.tiles_touched,
-                                                                                     local_screen_grads, peer_blocks);
+EGS_API int egs_push_rows(int32_t P, int32_t chunk_rows, int32_t world, int32_t rank, const void* geom,
+                          float* local_screen_grads, uint32_t* sent_counters, float* const* peer_inboxes,
+                          int32_t* const* peer_headers, void* stream) {
+    if (P < 0 || chunk_rows <= 0 || chunk_rows % PUSH_CTA != 0 || world <= 0 || world > 1024 || rank < 0 || rank >= world)
+        return EGS_E_BADARG;
+    if (!sent_counters || !peer_inboxes || !peer_headers) return EGS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P > 0) {
+        if (!geom || !local_screen_grads) return EGS_E_BADARG;
+        GeomView g = carve_geom(const_cast<void*>(geom), (size_t)P);
+        k_push_rows<<<(P + PUSH_CTA - 1) / PUSH_CTA, PUSH_CTA, 0, s>>>(P, chunk_rows, rank, g.tiles_touched,
+                                                                       local_screen_grads, sent_counters, peer_inboxes);
+        EGS_TRY(cudaGetLastError());
+    }
+    k_push_counts<<<1, 1024, 0, s>>>(world, rank, sent_counters, peer_headers);
+    EGS_TRY(cudaGetLastError());
+    return 0;
+}
+
+EGS_API int egs_fold_inbox(int32_t chunk_rows, int32_t world, int32_t first, const float* inbox, const int32_t* header,
+                           float* block, void* stream) {
+    if (chunk_rows <= 0 || world <= 0 || first < 0 || !inbox || !header || !block) return EGS_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    EGS_TRY(cudaMemsetAsync(block, 0, sizeof(float) * EGS_SCREEN_GRAD_STRIDE * (size_t)chunk_rows, s));
+    const int bx = (int)((4ll * chunk_rows + 255) / 256 < 1184 ? (4ll * chunk_rows + 255) / 256 : 1184);   // 148 SMs x 8
+    k_fold_inbox<<<dim3((unsigned)bx, (unsigned)world), 256, 0, s>>>(chunk_rows, first, inbox, header, block);
     EGS_TRY(cudaGetLastError());
     return 0;
 }

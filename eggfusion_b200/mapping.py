@@ -148,7 +148,9 @@ class FrameBatchOptimizer:
     NAMES = ("xyz", "features_dc", "features_rest", "scaling", "rotation", "opacity")
 
     def __init__(self, surfels, lr: LrParams, weights: MappingWeights = MappingWeights(), betas=(0.9, 0.999),
-                 eps: float = 1e-8):
+                 eps: float = 1e-8, padded_rows: Optional[int] = None):
+        """padded_rows (>= P): allocate the five tensors the renderer consumes with that many rows (the attributes stay
+        [P, ...] views), so that a sharded optimiser can all-gather them in place (parallel.DistributedMapper)."""
         self.lib = _lib.load()
         self.surfels = surfels
         get = (lambda n: surfels[n]) if isinstance(surfels, dict) else (lambda n: getattr(surfels, "_" + n))
@@ -162,15 +164,24 @@ class FrameBatchOptimizer:
         self.lr, self.weights, self.betas, self.eps = lr, weights, betas, eps
         P, M = self.P, self.M
         f32 = dict(dtype=torch.float32, device=dev)
+        rows = P if padded_rows is None else max(int(padded_rows), P)
+        self._full = {}
+
+        def alloc(name, *shape):
+            self._full[name] = torch.zeros((rows,) + shape, **f32)
+            return self._full[name][:P]
         # raw parameters; SH rows 0 / 1.. are _features_dc / _features_rest (identity activation: raw == activated)
-        self.xyz = src["xyz"].clone().contiguous()
-        self.shs = torch.cat([src["features_dc"], src["features_rest"]], dim=1).contiguous()
+        self.xyz = alloc("xyz", 3)
+        self.xyz.copy_(src["xyz"])
+        self.shs = alloc("shs", M, 3)
+        self.shs[:, :1].copy_(src["features_dc"])
+        self.shs[:, 1:].copy_(src["features_rest"])
         self.scaling_raw = src["scaling"].clone().contiguous()
         self.rotation_raw = src["rotation"].clone().contiguous()
         self.opacity_raw = src["opacity"].clone().contiguous()
         # activated
-        self.opacity, self.scales = torch.empty((P, 1), **f32), torch.empty((P, 3), **f32)
-        self.rotations, self.normal0 = torch.empty((P, 4), **f32), torch.empty((P, 3), **f32)
+        self.opacity, self.scales = alloc("opacity", 1), alloc("scales", 3)
+        self.rotations, self.normal0 = alloc("rotations", 4), torch.empty((P, 3), **f32)
         # Adam state
         self.state = {n: (torch.zeros_like(t), torch.zeros_like(t)) for n, t in
                       (("xyz", self.xyz), ("shs", self.shs), ("opacity", self.opacity_raw),

@@ -57,9 +57,17 @@ def tile_partition(tiles_y: int, tiles_x: int, world: int, rank: int,
     return mask
 
 
+CHUNK_ALIGN = 256   # rows; a rank's surfel range starts at a multiple of it (egs_push_rows works on 256-surfel groups)
+
+
 def padded_rows(P: int, world: int) -> int:
-    """Rows of the exchanged block: P rounded up so every rank owns the same number of rows."""
-    return (P + world - 1) // world * world
+    """Rows of the exchanged block: every rank owns the same number of rows (`padded_rows // world`), a multiple of
+    CHUNK_ALIGN when the block is split at all."""
+    if world <= 1:
+        return P
+    chunk = (P + world - 1) // world
+    chunk = (chunk + CHUNK_ALIGN - 1) // CHUNK_ALIGN * CHUNK_ALIGN
+    return chunk * world
 
 
 def surfel_range(P: int, world: int, rank: int) -> Tuple[int, int]:
@@ -89,23 +97,32 @@ def reduce_scatter_rows(block: torch.Tensor, group=None) -> torch.Tensor:
     return tmp[rank * chunk:(rank + 1) * chunk].contiguous()
 
 
-def all_gather_rows(t: torch.Tensor, first: int, count: int, chunk: int, world: int, group=None, cache=None) -> None:
+def all_gather_rows(t: torch.Tensor, first: int, count: int, chunk: int, world: int, group=None, cache=None,
+                    full: Optional[torch.Tensor] = None) -> None:
     """In place: every rank's owned rows [first, first + count) of `t` ([P, ...], same shape everywhere) are
-    distributed to all ranks.  One all_gather_into_tensor of equal padded chunks (NCCL); gloo (CPU tests) gathers a list."""
+    distributed to all ranks.  `full`: the [world * chunk, ...] allocation `t` is the head of (FrameBatchOptimizer with
+    padded_rows): one in-place all_gather_into_tensor, no staging.  Otherwise equal padded chunks are staged; gloo (CPU
+    tests) gathers a list."""
     P = t.shape[0]
     flat = t.view(P, -1)
+    nccl = dist.get_backend(group) == "nccl"
+    if full is not None and nccl and full.shape[0] == world * chunk and full.data_ptr() == t.data_ptr():
+        f2 = full.view(world * chunk, -1)
+        rank = dist.get_rank(group)
+        dist.all_gather_into_tensor(f2, f2[rank * chunk:(rank + 1) * chunk], group=group)
+        return
     key = (flat.shape[1], flat.dtype)
     cache = {} if cache is None else cache
     if key not in cache:
         cache[key] = (torch.zeros((chunk, flat.shape[1]), dtype=flat.dtype, device=flat.device),
                       torch.empty((world * chunk, flat.shape[1]), dtype=flat.dtype, device=flat.device))
-    mine, full = cache[key]
+    mine, staged = cache[key]
     mine[:count].copy_(flat[first:first + count])
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(full, mine, group=group)
+    if nccl:
+        dist.all_gather_into_tensor(staged, mine, group=group)
     else:
-        dist.all_gather(list(full.view(world, chunk, -1).unbind(0)), mine, group=group)
-    flat.copy_(full[:P])
+        dist.all_gather(list(staged.view(world, chunk, -1).unbind(0)), mine, group=group)
+    flat.copy_(staged[:P])
 
 
 def _world_rank(group=None) -> Tuple[int, int]:
@@ -116,14 +133,17 @@ def _world_rank(group=None) -> Tuple[int, int]:
 
 # ------------------------------------------------------------------------------------------------- the exchange
 class PeerExchange:
-    """Owner-side accumulation blocks of the screen-gradient exchange in NVLink peer (symmetric) memory.
+    """The screen-gradient exchange of a tile-sharded step over NVLink peer (symmetric) memory.
 
-    Two blocks of padded_rows(P)/world rows x 16 floats alternate between steps: rank r's block `b` receives, from every
-    rank, the rows of its surfel range that the sender's reverse walk touched (`push`), `barrier` orders the pushes of
-    all ranks before the owner reads, and the owner clears the block once its per-surfel backward has consumed it.
-    A block is pushed to again two steps later, after at least one more barrier that its owner joins only after the
-    clear (stream order), so one device-side barrier per step is enough.
+    Every rank owns an INBOX per parity (symmetric memory, peers store into it): a header of `world` row counts and
+    [world senders][chunk rows][16 floats].  A step: `push` (egs_push_rows: the rows this rank's reverse walk touched
+    are compacted per 256-surfel group and streamed into the owners' inboxes with coalesced stores; the local rows are
+    cleared), `barrier` (device-side, all ranks), `fold` (egs_fold_inbox: the owner adds what the senders left into
+    its block).  An inbox is written again two steps later, after at least one more barrier that its owner joins only
+    after the fold (stream order), so one barrier per step is enough.
     """
+
+    HEAD = 256   # bytes reserved for the header in front of the inbox
 
     def __init__(self, P: int, device, group=None):
         import torch.distributed._symmetric_memory as symm
@@ -132,43 +152,53 @@ class PeerExchange:
         self.group = dist.group.WORLD if group is None else group
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.P = int(P)
-        self.chunk = padded_rows(P, self.world) // self.world
+        self.chunk = max(padded_rows(P, self.world) // self.world, CHUNK_ALIGN)
+        self.first = min(self.P, self.rank * self.chunk)
         self.device = torch.device(device)
         name = self.group.group_name
         try:
             symm.enable_symm_mem_for_group(name)
         except Exception:
             pass
+        nfl = self.HEAD // 4 + self.world * self.chunk * SCREEN_GRAD_STRIDE
         with torch.cuda.device(self.device):
-            self.blocks = [symm.empty((max(self.chunk, 1), SCREEN_GRAD_STRIDE), dtype=torch.float32, device=self.device)
-                           for _ in range(2)]
-            self.handles = [symm.rendezvous(b, name) for b in self.blocks]
-            for b in self.blocks:
-                b.zero_()
-            # device arrays of the world's block addresses as this process maps them
-            self.tables = [torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=self.device)
-                           for h in self.handles]
+            self.buffers = [symm.empty((nfl,), dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.handles = [symm.rendezvous(b, name) for b in self.buffers]
+            for b in self.buffers:
+                b[:self.HEAD // 4].zero_()
+            i64 = dict(dtype=torch.int64, device=self.device)
+            # device arrays of the world's header / inbox addresses as this process maps them
+            self.headers = [torch.tensor([int(p) for p in h.buffer_ptrs], **i64) for h in self.handles]
+            self.inboxes = [torch.tensor([int(p) + self.HEAD for p in h.buffer_ptrs], **i64) for h in self.handles]
+            self.sent = torch.zeros((self.world,), dtype=torch.int32, device=self.device)
+            self.block = torch.empty((self.chunk, SCREEN_GRAD_STRIDE), dtype=torch.float32, device=self.device)
             torch.cuda.synchronize(self.device)
         dist.barrier(self.group)
         self.parity = 0
 
-    def push(self, geom: torch.Tensor, local_sg: torch.Tensor, stream: int) -> None:
+    def exchange(self, geom: torch.Tensor, local_sg: torch.Tensor, stream: int, mark=None) -> int:
+        """push + barrier + fold.  Returns the address at which row 0 of the FULL [P][16] block would lie if the owned
+        block were a window into it (the per-surfel kernel indexes by global surfel id)."""
         from . import _lib
-        _lib.check(self.lib.egs_push_rows(self.P, self.chunk, geom.data_ptr(), local_sg.data_ptr(),
-                                          self.tables[self.parity].data_ptr(), stream), "push_rows")
-
-    def barrier(self) -> None:
-        self.handles[self.parity].barrier(channel=0)
-
-    def owned_base(self) -> int:
-        """Address at which row 0 of the FULL [P][16] block would lie if the owned block were a window into it (the
-        per-surfel kernel indexes by global surfel id)."""
-        return self.blocks[self.parity].data_ptr() - self.rank * self.chunk * SCREEN_GRAD_STRIDE * 4
+        b = self.parity
+        self.parity ^= 1
+        _lib.check(self.lib.egs_push_rows(self.P, self.chunk, self.world, self.rank, geom.data_ptr(), local_sg.data_ptr(),
+                                          self.sent.data_ptr(), self.inboxes[b].data_ptr(), self.headers[b].data_ptr(),
+                                          stream), "push_rows")
+        if mark:
+            mark("push_rows")
+        self.handles[b].barrier(channel=0)
+        if mark:
+            mark("barrier")
+        buf = self.buffers[b]
+        _lib.check(self.lib.egs_fold_inbox(self.chunk, self.world, self.first, buf.data_ptr() + self.HEAD, buf.data_ptr(),
+                                           self.block.data_ptr(), stream), "fold_inbox")
+        if mark:
+            mark("fold_inbox")
+        return self.block.data_ptr() - self.first * SCREEN_GRAD_STRIDE * 4
 
     def consumed(self) -> None:
-        """The owner has read the block: clear it and move on to the other one."""
-        self.blocks[self.parity].zero_()
-        self.parity ^= 1
+        """Kept for symmetry with the reduce-scatter path: egs_fold_inbox rewrites the whole block."""
 
 
 def make_exchange(P: int, device, group=None) -> Optional[PeerExchange]:
@@ -249,9 +279,7 @@ class ShardedSplat:
             first, count = surfel_range(P, self.world, self.rank)
             keep = sg
             if self.world > 1 and ex is not None:
-                ex.push(st.geom, sg, stream)
-                ex.barrier()
-                base = ex.owned_base()
+                base = ex.exchange(st.geom, sg, stream)
             elif self.world > 1:
                 keep = reduce_scatter_rows(sg, self.group)
                 # the per-surfel kernel indexes the block by global surfel id: view the chunk at its global offset
@@ -364,8 +392,10 @@ class DistributedMapper:
         # all-gather staging: one padded [world * chunk, 59 or so] buffer per activated tensor
         self._gather = {}
 
-    def _all_gather_rows(self, t: torch.Tensor) -> None:
-        all_gather_rows(t, self.first, self.count, self.chunk, self.world, self.group, self._gather)
+    def _all_gather_rows(self, name: str) -> None:
+        o = self.opt
+        all_gather_rows(getattr(o, name), self.first, self.count, self.chunk, self.world, self.group, self._gather,
+                        full=o._full.get(name))
 
     def iterate(self, settings, frame_input, render_mask):
         from . import _lib, mapping as MP, rasterizer as R
@@ -383,9 +413,7 @@ class DistributedMapper:
                 ctx.backward_render(self.g_color, self.g_normal, self.g_depth, self.g_opac, prezeroed=self.exchange is not None)
                 stream = R._stream_ptr(o.device)
                 if self.exchange is not None:
-                    self.exchange.push(ctx.geom, ctx.screen, stream)
-                    self.exchange.barrier()
-                    base = self.exchange.owned_base()
+                    base = self.exchange.exchange(ctx.geom, ctx.screen, stream)
                 else:
                     mine = reduce_scatter_rows(ctx.screen, self.group)
                     base = mine.data_ptr() - self.rank * self.chunk * SCREEN_GRAD_STRIDE * 4
@@ -404,7 +432,7 @@ class DistributedMapper:
                 part = self.terms[1:5].clone()
                 dist.all_reduce(part, group=self.group)
                 self.terms[1:5] = part
-                for t in (o.xyz, o.shs, o.opacity, o.scales, o.rotations):
-                    self._all_gather_rows(t)
+                for name in ("xyz", "shs", "opacity", "scales", "rotations"):
+                    self._all_gather_rows(name)
             return o.loss_values(self.terms, frame_input.get("depth_map") is not None,
                                  frame_input.get("normal_map_c") is not None)

@@ -123,16 +123,25 @@ EGS_API int egs_forward_plan_sharded(const egs_frame* frame, const float* means3
                                      egs_counters* counters_host, void* stream);
 
 /*
- * Exchange step of a tile-sharded frame over peer memory (one process per GPU, NVLink / NVSwitch): adds the rows of
- * `local_screen_grads` [P][16] that this rank's reverse walk touched to their owners' accumulation blocks and clears
- * them locally.  peer_blocks: DEVICE array of world_size pointers, peer_blocks[r] = rank r's block of `chunk_rows` rows
- * for surfels [r * chunk_rows, (r+1) * chunk_rows) (peer-mapped addresses; r == own rank: the local block).  The
- * caller orders it against the owners' readers (a barrier after this call on every rank).  Replaces a dense NCCL
- * reduce-scatter of the whole block: only touched rows cross the links, as 16-byte reductions performed by the
- * owner's L2.
+ * Exchange step of a tile-sharded frame over peer memory (one process per GPU, NVLink / NVSwitch), sender side: moves
+ * the rows of `local_screen_grads` [P][16] that this rank's reverse walk touched into this sender's section of their
+ * owners' inboxes (compacted per 256-surfel group, streamed with coalesced stores on peer-mapped addresses; the surfel
+ * id travels in the row's last padding word), clears them locally and publishes the per-owner row counts.
+ * Owner r owns surfels [r * chunk_rows, (r+1) * chunk_rows); chunk_rows must be a multiple of 256.
+ * peer_inboxes / peer_headers: DEVICE arrays of `world` pointers to rank r's inbox (float [world][chunk_rows][16]) and
+ * header (int32 [world]) as THIS process maps them.  sent_counters: device uint32 [world], zero before the first call
+ * (the call leaves it zero).
+ * The caller orders it against the owners' readers: a barrier after this call on every rank, then egs_fold_inbox.
+ * Replaces a dense NCCL reduce-scatter of the whole block: only touched rows cross the links.
  */
-EGS_API int egs_push_rows(int32_t num_surfels, int32_t chunk_rows, const void* geom, float* local_screen_grads,
-                          float* const* peer_blocks, void* stream);
+EGS_API int egs_push_rows(int32_t num_surfels, int32_t chunk_rows, int32_t world, int32_t rank, const void* geom,
+                          float* local_screen_grads, uint32_t* sent_counters, float* const* peer_inboxes,
+                          int32_t* const* peer_headers, void* stream);
+
+/* Owner side of the exchange: block (float [chunk_rows][16], the accumulation block of surfels
+ * [first, first + chunk_rows)) = sum of the rows the `world` senders left in `inbox` (header[s] rows from sender s). */
+EGS_API int egs_fold_inbox(int32_t chunk_rows, int32_t world, int32_t first, const float* inbox, const int32_t* header,
+                           float* block, void* stream);
 
 /*
  * Instance emission, per-tile depth sort and front-to-back compositing.  `bin` must hold `cap_instances`

@@ -125,7 +125,8 @@ def main():
                         t(scene["rotations"]), None)
     cap = int(out[6].num_rendered * 1.3) + 4096
     del out
-    mopt = MP.FrameBatchOptimizer(raw, MP.LrParams(**bench.MAP_LR), MP.MappingWeights(**bench.MAP_WEIGHTS))
+    mopt = MP.FrameBatchOptimizer(raw, MP.LrParams(**bench.MAP_LR), MP.MappingWeights(**bench.MAP_WEIGHTS),
+                                  padded_rows=par.padded_rows(P, world))
     dm = par.DistributedMapper(mopt, W, H, cap, deg_b)
     losses = []
     for i in range(iters):

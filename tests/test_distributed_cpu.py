@@ -37,7 +37,8 @@ def test_surfel_ranges_cover_exactly():
     for P in (0, 1, 7, 1000, 1_000_003):
         for world in (1, 2, 4, 8):
             rows = par.padded_rows(P, world)
-            assert rows % world == 0 and rows >= P and rows - P < world
+            assert rows % world == 0 and rows >= P and rows - P < world * par.CHUNK_ALIGN
+            assert world == 1 or (rows // world) % par.CHUNK_ALIGN == 0
             spans = [par.surfel_range(P, world, r) for r in range(world)]
             covered = 0
             for first, count in spans:
