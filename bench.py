@@ -453,6 +453,36 @@ def reference_tracking_frame_factory(model, frame, T0):
     return track
 
 
+# ------------------------------------------------------------------------------------------------ the reference's own loop
+def slam_loop(arm, frames=24):
+    """BASELINE configs 2 and 5: frames/s of the reference's UNMODIFIED Python loop (oracle/_ref/egg, byte copy of
+    /root/reference/src: EGGFusion.reconstruct = tracking + fusion + mapping + postprocess per frame) on a synthetic RGB-D
+    sequence at the Replica (1200x680, SH 3) and TUM fr1 (640x480, SH 0) calibrations, on top of `arm`'s native back end
+    (tests/ref_loop.py; ours = eggfusion_b200/dropin, reference = oracle/_ref builds).  Steady state = frames 4.. ."""
+    import subprocess
+    import tempfile
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "egg", "src")):
+        return None
+    out = {}
+    for config in ("replica", "tum"):
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "loop.npz")
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_loop.py"), "--arm", arm, "--config", config,
+                                "--frames", str(frames), "--out", path], capture_output=True, text=True, cwd=ROOT)
+            if r.returncode != 0:
+                out[config] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            d = np.load(path)
+            steady = d["wall"][4:]
+            out[config] = {"frames": int(len(d["wall"])), "ms_per_frame": 1e3 * float(steady.mean()),
+                           "frames_per_s": 1.0 / float(steady.mean()), "ate_rmse_m": float(d["ate"]),
+                           "surfels": int(d["n_surfels"])}
+    out["what"] = ("the reference's own main.py loop, unmodified, on a synthetic RGB-D sequence (datasets absent offline; "
+                   "use_sparse False: ORB-SLAM2 un-buildable), native back end: " +
+                   ("eggfusion_b200/dropin (this repository)" if arm == "ours" else "oracle/_ref (the reference's CUDA builds)"))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_baseline_sample(scene, cams, grads, deg, budget_s=12.0):
     """Oracle port (C, OpenMP, all host cores) on a bounded sample of the same workload: whole frames (forward +
@@ -868,6 +898,10 @@ def run_ours(args):
         line["c4"] = c4
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)
+    if world == 1 and not args.no_loop:
+        del main_run
+        torch.cuda.empty_cache()
+        line["slam_loop"] = slam_loop("ours")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -1022,6 +1056,9 @@ def run_reference(args):
         "mapping_iter": mapping,
         "tracking_frame": tracking,
     }
+    if not args.no_loop:
+        torch.cuda.empty_cache()
+        line["slam_loop"] = slam_loop("reference")
     print(json.dumps(line))
 
 
@@ -1039,6 +1076,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mapping", action="store_true")
     ap.add_argument("--no-tracking", action="store_true")
+    ap.add_argument("--no-loop", action="store_true", help="skip the reference-loop frames/s (configs 2 and 5)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

@@ -236,3 +236,44 @@ def make_fusion_case(P: int, cam: Camera, seed: int = SEED + 7, alpha_p: float =
         "intrinsic": f32([cam.fx, cam.fy, cam.cx, cam.cy]), "frame_vmap": f32(vmap), "frame_nmap": f32(nmap),
         "frame_dmap": f32(dmap), "frame_mask": mask, "fusion_dist_thres": 0.03, "alpha_p": alpha_p, "alpha_n": alpha_n,
     }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Synthetic RGB-D sequence (BASELINE configs 2 and 5: the datasets are absent offline): a camera on a smooth
+# 6-DoF trajectory looking at a textured, gently curved wall, at a dataset's calibration.  Exact depth by ray / surface
+# intersection, procedural colour; what /root/reference/src/utils/dataset.py's RGBDDataset.__getitem__ returns per frame
+# (timestamp, uint8 colour [H,W,3], integer depth [H,W] in 1/depth_scale m, bool mask [H,W,1], 4x4 world-to-camera pose
+# relative to the first frame) so that /root/reference/src/utils/frame.py:149 `Frame.init_from_dataset` consumes it.
+def _wall_z(x, y):
+    return 2.0 + 0.25 * np.sin(1.3 * x + 0.4) * np.cos(1.1 * y - 0.2) + 0.08 * np.sin(3.1 * x) * np.sin(2.7 * y)
+
+
+def _wall_color(x, y):
+    r = 0.5 + 0.35 * np.sin(9.0 * x + 1.0) * np.cos(7.0 * y) + 0.1 * np.sin(31.0 * x + 17.0 * y)
+    g = 0.5 + 0.35 * np.cos(8.0 * x - 2.0 * y) + 0.1 * np.sin(23.0 * y - 5.0 * x)
+    b = 0.5 + 0.3 * np.sin(6.0 * y + 0.5) * np.sin(5.0 * x + 3.0 * y) + 0.15 * np.cos(27.0 * x)
+    return np.clip(np.stack([r, g, b], axis=-1), 0.0, 1.0)
+
+
+def rgbd_pose(i: int) -> np.ndarray:
+    """World-to-camera pose of frame i (frame 0 = identity): ~4 mm and ~0.15 degrees per frame."""
+    tx, ty, tz = 0.004 * i, 0.0015 * math.sin(0.3 * i), 0.002 * i
+    c2w = np.linalg.inv(look_from((tx, ty, tz), 0.0026 * i, -0.0012 * i).astype(np.float64))
+    return np.linalg.inv(c2w)
+
+
+def make_rgbd_frame(i: int, width: int, height: int, fx: float, fy: float, cx: float, cy: float, depth_scale: float):
+    w2c = rgbd_pose(i)
+    c2w = np.linalg.inv(w2c)
+    v, u = np.meshgrid(np.arange(height, dtype=np.float64), np.arange(width, dtype=np.float64), indexing="ij")
+    d = np.stack([(u - cx) / fx, (v - cy) / fy, np.ones_like(u)], axis=-1) @ c2w[:3, :3].T     # ray directions, world
+    o = c2w[:3, 3]
+    s = np.full(u.shape, 2.0)                       # ray parameter (camera-frame depth, since d.z_cam = 1)
+    for _ in range(12):                             # fixed point of  o.z + s d.z = wall(o.xy + s d.xy)
+        p = o + s[..., None] * d
+        s = (_wall_z(p[..., 0], p[..., 1]) - o[2]) / d[..., 2]
+    p = o + s[..., None] * d
+    color = (np.clip(_wall_color(p[..., 0], p[..., 1]), 0, 1) * 255.0 + 0.5).astype(np.uint8)
+    depth = np.clip(np.rint(s * depth_scale), 0, 65535).astype(np.uint16)
+    mask = np.ones((height, width, 1), dtype=bool)
+    return 0.05 * i, color, depth, mask, w2c

@@ -36,3 +36,14 @@ if [ -d "$TRK_SRC" ] && ! ls "$OUT"/cuda_tracking_ext*.so >/dev/null 2>&1; then
     cp "$TW"/cuda_tracking_ext*.so "$OUT/"
     echo "built $OUT (tracking util, Eigen stubbed)"
 fi
+
+# --- the reference's own Python (core loop + configs), byte for byte, so that the loop test can run it UNMODIFIED on
+# the GPU box (where /root/reference does not exist) on top of either rasterizer.  Git-ignored like the rest of _ref.
+EGG_SRC="${REFERENCE_ROOT:-/root/reference}"
+if [ -d "$EGG_SRC/src" ] && { [ ! -d "$OUT/egg/src" ] || [ -n "${FORCE:-}" ]; }; then
+    rm -rf "$OUT/egg" && mkdir -p "$OUT/egg"
+    cp -r "$EGG_SRC/src" "$EGG_SRC/configs" "$EGG_SRC/main.py" "$OUT/egg/"
+    find "$OUT/egg" -name "__pycache__" -type d -prune -exec rm -rf {} + 2>/dev/null || true
+    rm -rf "$OUT/egg/src/utils/cuda/src" "$OUT/egg/src/utils/cuda/build" 2>/dev/null || true   # CUDA sources stay where they are
+    echo "copied the reference's src/ and configs/ to $OUT/egg"
+fi
