@@ -453,6 +453,52 @@ def reference_tracking_frame_factory(model, frame, T0):
     return track
 
 
+# ------------------------------------------------------------------------------------------------ frame ingest (N4)
+def ingest_inputs(dev, W=1200, H=680):
+    """One RGB-D frame at the Replica size: colour [H,W,3], unfiltered depth [H,W,1], float mask [H,W,1], intrinsics."""
+    import torch
+    r = np.random.default_rng(41)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    depth = 2.0 + 0.3 * np.sin(xx / W * 5) * np.cos(yy / H * 4) + 0.002 * r.standard_normal((H, W))
+    color = np.clip(np.stack([0.5 + 0.4 * np.sin(xx * 0.09), 0.5 + 0.4 * np.cos(yy * 0.07), 0.5 + 0.3 * np.sin((xx + yy) * 0.05)],
+                             -1) + 0.02 * r.standard_normal((H, W, 3)), 0, 1)
+    mask = (r.uniform(0, 1, (H, W, 1)) < 0.98).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    return t(color), t(depth[..., None]), t(mask), (600.0, 600.0, (W - 1) / 2.0, (H - 1) / 2.0)
+
+
+def ingest_algorithmic_bytes(W, H, nlevel=3):
+    """Bytes the ingest chain must move at least once: level 0 reads colour 12 + depth 4 + mask 4 and writes depth 4 +
+    disp 4 + mask 1 + maskf 4 + vertex 12 + normal 12 + grey 4 + grad 12 per pixel; every further level re-reads grey /
+    depth / maskf / vertex / normal of its parent (36 B per parent pixel) and writes the same 53 B per pixel."""
+    total, w, h = 0, W, H
+    for l in range(nlevel):
+        total += w * h * 53 + (w * h * 20 if l == 0 else (2 * w) * (2 * h) * 36)
+        w, h = w // 2, h // 2
+    return total
+
+
+def reference_ingest_factory(dev, color, depth_raw, mask, intr):
+    """Frame.__init__'s bilateral + PyraImageCUDA (src/utils/frame.py:132,32-99): the reference's OWN class from
+    oracle/_ref/egg on the reference's own build of cuda_tracking_ext (tests/shims_ref)."""
+    import torch
+    egg = os.path.join(ROOT, "oracle", "_ref", "egg")
+    if not os.path.isdir(os.path.join(egg, "src")):
+        return None
+    for p_ in (os.path.join(ROOT, "tests", "shims"), os.path.join(ROOT, "oracle", "_ref"),
+               os.path.join(ROOT, "tests", "shims_ref"), egg):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    from src.utils.frame import PyraImageCUDA
+    from src.utils.cuda import bilateral_filter
+    intr_t = torch.tensor(intr)
+
+    def ingest(_i):
+        depth = bilateral_filter(depth_raw, 13, 0.03, 4.5)
+        return PyraImageCUDA(color, depth, mask, intr_t, 3, dev)
+    return ingest
+
+
 # ------------------------------------------------------------------------------------------------ the reference's own loop
 def slam_loop(arm, frames=24):
     """BASELINE configs 2 and 5: frames/s of the reference's UNMODIFIED Python loop (oracle/_ref/egg, byte copy of
@@ -637,10 +683,16 @@ def run_ours(args):
             dist.all_reduce(Isum, op=dist.ReduceOp.SUM)
         ms_step = float(tmax.item()) / args.steps
         I_total = float(Isum.item())
+        # the workload's instance count as a property of the scene (mean over its cameras, independent of --steps)
+        Iall = torch.tensor([float(np.mean(I_cam))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(Iall, op=dist.ReduceOp.SUM)
+        I_all = float(Iall.item())
         del ctx
         return dict(scene=scene, cams=cams, grads=grads, deg=deg, P=P, M=M, W=W, H=H, params=params, bg=bg,
                     settings=settings, mask=mask, costs=costs, cap=cap, stage_ms=stage_ms, I_mean=I_mean,
                     vis_mean=vis_mean, ms_step=ms_step, I_total=I_total, clocks=clocks, exchange=exch,
+                    I_all_cams=I_all,
                     value=256.0 * I_total / (ms_step * 1e-3) / 1e6)
 
     main_run = device_resident(args.workload)
@@ -837,6 +889,18 @@ def run_ours(args):
               "instances_per_frame": r4["I_total"], "stage_ms": r4["stage_ms"],
               "exchange": "nvlink peer memory (egs_push_rows)" if r4["exchange"] is not None else "nccl reduce_scatter"}
         r4.clear()
+    ingest = None
+    if world == 1 and not args.no_tracking:
+        from eggfusion_b200 import tracking as TRK
+        ic, idp, im_, iintr = ingest_inputs(dev)
+        fi = TRK.FrameIngest(1200, 680, 3, device=dev)
+        ms_ing = time_loop(lambda i: fi(ic, idp, im_, iintr), max(3, args.warmup), args.steps)
+        ib = ingest_algorithmic_bytes(1200, 680)
+        ingest = {"ms_per_frame": ms_ing, "frames_per_s": 1e3 / ms_ing, "algorithmic_bytes": ib,
+                  "hbm_frac": ib / (ms_ing * 1e-3) / 1e9 / hbm_peak()[0],
+                  "what": "Frame.__init__ bilateral + PyraImageCUDA of one 1200x680 RGB-D frame, 3 levels = "
+                          "eggfusion_b200.tracking.FrameIngest (egt_ingest_frame: 3 launches, no device sync; 169 IEEE expf "
+                          "per pixel keep it SFU / issue bound)", "gpu_launches_per_frame": 3}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -873,7 +937,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args.workload, P, W, H, deg, M, I_total),
+        "config": config_dict(args.workload, P, W, H, deg, M, main_run["I_all_cams"]),
         "parallelism": "tiles%d" % world if world > 1 else "single", "visible_surfels": vis_mean,
         "frames_per_s": 1e3 / ms_step,
         "nominal_surfel_pixels_per_s_M": P * N_px / (ms_step * 1e-3) / 1e6,
@@ -890,6 +954,7 @@ def run_ours(args):
         "e2e_eager": e2e_eager,
         "mapping_iter": mapping,
         "tracking_frame": tracking,
+        "frame_ingest": ingest,
     }
     if world > 1:
         line["exchange"] = ("nvlink peer memory (egs_push_rows: the touched rows stored into the owners' inboxes, device "
@@ -899,7 +964,6 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)
     if world == 1 and not args.no_loop:
-        del main_run
         torch.cuda.empty_cache()
         line["slam_loop"] = slam_loop("ours")
     print(json.dumps(line))
@@ -1039,12 +1103,21 @@ def run_reference(args):
                     "dense_delta_t": [float(v) for v in last["T"][:3, 3]],
                     "what": "dense part of Tracker.tracking_frame with the reference's PyTorch flow (projective_transform, "
                             "icp_optimization, rgb_optimization, CPU solve, .item() convergence test)"}
+    ingest = None
+    if not args.no_tracking:
+        ic, idp, im_, iintr = ingest_inputs(dev)
+        fn = reference_ingest_factory(dev, ic, idp, im_, iintr)
+        if fn is not None:
+            ms_ing = time_loop(fn, max(3, args.warmup), max(5, args.steps // 5))
+            ingest = {"ms_per_frame": ms_ing, "frames_per_s": 1e3 / ms_ing,
+                      "what": "Frame.__init__ bilateral + the reference's own PyraImageCUDA (oracle/_ref/egg/src/utils/frame.py) "
+                              "on its own cuda_tracking_ext build, one 1200x680 frame, 3 levels"}
     line = {
         "impl": "reference", "device": "cuda (unmodified diff-gaussian-surfels compiled for sm_100a, oracle/_ref)",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": config_dict(args.workload, P, W, H, deg, M, I_mean),
+        "config": config_dict(args.workload, P, W, H, deg, M, float(np.mean(I_cam))),
         "frames_per_s": 1e3 / ms_step, "clocks": clocks,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                          "sample": "full workload; the reference has no CPU implementation of this path, so its own "
@@ -1055,6 +1128,7 @@ def run_reference(args):
                 "api": "diff_gaussian_rasterization.GaussianRasterizer + torch L1 loss + loss.backward() + loss.item()"},
         "mapping_iter": mapping,
         "tracking_frame": tracking,
+        "frame_ingest": ingest,
     }
     if not args.no_loop:
         torch.cuda.empty_cache()

@@ -73,10 +73,18 @@ class Level(C.Structure):
                 ("frame_intensity", C.c_void_p), ("frame_grad", C.c_void_p)]
 
 
+class PyramidLevel(C.Structure):
+    """struct egt_pyramid_level"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("depth", C.c_void_p), ("disp", C.c_void_p),
+                ("mask", C.c_void_p), ("maskf", C.c_void_p), ("vertex", C.c_void_p), ("normal", C.c_void_p),
+                ("gray", C.c_void_p), ("grad", C.c_void_p)]
+
+
 EGT_GN_SUMS = 56
 SIGNATURES.update({
     "egt_gn_accumulate": (C.c_int, [C.POINTER(Level), _P, C.c_float, C.c_float, _I32, _P, _P]),
     "egt_gn_solve_update": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
+    "egt_ingest_frame": (C.c_int, [_P, _P, _P, _I32, _I32] + [C.c_float] * 6 + [_I32, C.POINTER(PyramidLevel), _P]),
     "egt_track_pyramid": (C.c_int, [_P, _I32, _P, C.c_float, C.c_float, _I32, C.c_float, C.c_float, C.c_float,
                                     C.c_float, _P, _P, _P, _P, _P, _P]),
 })

@@ -111,3 +111,74 @@ class DenseTracker:
         self.last_dense_delta = dense_delta   # the optimised delta, whether or not it is committed
         curr = torch.where(conv, dense_delta @ prev_transform, delta_transform @ prev_transform)
         return curr, conv
+
+
+class FramePyramid:
+    """What PyraImageCUDA (src/utils/frame.py:22-99) holds for one frame, produced by ONE call (`ingest_frame`):
+    the same attribute lists (`DenseTracker` and the reference's optimizer functions consume it as is) plus the
+    level-0 maps Frame / PyraImageCUDA expose (`depth`, `vmap`, `nmap`, `gray`)."""
+
+    def __init__(self, nlevel):
+        self.nlevel = nlevel
+        self.intensity_pyramid, self.intrinsic_pyramid, self.disp_pyramid, self.grad_pyramid = [], [], [], []
+        self.mask_pyramid, self.vertex_pyramid, self.normal_pyramid, self.depth_pyramid = [], [], [], []
+
+
+class FrameIngest:
+    """Persistent buffers + the fused ingest chain (egt_ingest_frame) for frames of one size.
+
+        ingest = FrameIngest(width, height, nlevel=3)
+        pyr = ingest(color, depth_raw, mask, intr)        # nlevel launches, no device sync, no allocation
+
+    color [H,W,3] float32 in 0..1, depth_raw [H,W,1] or [H,W] float32 metres (UNFILTERED: the 13x13 bilateral of
+    Frame.__init__ is part of the chain), mask [H,W,1] or [H,W] float32.  The returned lists alias the persistent buffers:
+    they are overwritten by the next call (use `clone_outputs=True` to keep them)."""
+
+    def __init__(self, width: int, height: int, nlevel: int = 3, device="cuda:0", sigma_color: float = 0.03,
+                 sigma_space: float = 4.5):
+        self.lib = _lib.load()
+        self.W, self.H, self.nlevel = int(width), int(height), int(nlevel)
+        self.device = torch.device(device)
+        self.sigma_color, self.sigma_space = float(sigma_color), float(sigma_space)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.buf = []
+        w, h = self.W, self.H
+        for _l in range(self.nlevel):
+            if w == 0 or h == 0:
+                raise ValueError("image too small for %d pyramid levels" % nlevel)
+            self.buf.append({"depth": torch.empty((h, w, 1), **f32), "disp": torch.empty((h, w, 1), **f32),
+                             "mask": torch.empty((h, w, 1), dtype=torch.bool, device=self.device),
+                             "maskf": torch.empty((h, w, 1), **f32), "vertex": torch.empty((h, w, 3), **f32),
+                             "normal": torch.empty((h, w, 3), **f32), "gray": torch.empty((h, w, 1), **f32),
+                             "grad": torch.empty((h, w, 3), **f32)})
+            w, h = w // 2, h // 2
+        self.levels = (_lib.PyramidLevel * self.nlevel)(*[
+            _lib.PyramidLevel(b["depth"].shape[1], b["depth"].shape[0], b["depth"].data_ptr(), b["disp"].data_ptr(),
+                              b["mask"].data_ptr(), b["maskf"].data_ptr(), b["vertex"].data_ptr(), b["normal"].data_ptr(),
+                              b["gray"].data_ptr(), b["grad"].data_ptr()) for b in self.buf])
+
+    def __call__(self, color, depth_raw, mask, intr, clone_outputs: bool = False) -> FramePyramid:
+        color, depth_raw, mask = _f32(color, "color"), _f32(depth_raw, "depth_raw"), _f32(mask, "mask")
+        if color.numel() != 3 * self.W * self.H or depth_raw.numel() != self.W * self.H or mask.numel() != self.W * self.H:
+            raise RuntimeError("ingest_frame: inputs must be [H, W, C] of the size the FrameIngest was built for")
+        fx, fy, cx, cy = [float(v) for v in intr]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.egt_ingest_frame(color.data_ptr(), depth_raw.data_ptr(), mask.data_ptr(), self.W, self.H,
+                                                 fx, fy, cx, cy, self.sigma_color, self.sigma_space, self.nlevel,
+                                                 self.levels, R._stream_ptr(self.device)), "ingest_frame")
+        pyr = FramePyramid(self.nlevel)
+        get = (lambda t: t.clone()) if clone_outputs else (lambda t: t)
+        for l, b in enumerate(self.buf):
+            pyr.intensity_pyramid.append(get(b["gray"]))
+            pyr.disp_pyramid.append(get(b["disp"]))
+            pyr.grad_pyramid.append(get(b["grad"]))
+            pyr.mask_pyramid.append(get(b["mask"]))
+            pyr.vertex_pyramid.append(get(b["vertex"]))
+            pyr.normal_pyramid.append(get(b["normal"]))
+            pyr.depth_pyramid.append(get(b["depth"]))
+            # frame.py:80-81 divides the PREVIOUS level's intrinsics by 2^l (so level 2 = level 0 / 8): kept
+            prev = pyr.intrinsic_pyramid[-1] if l else torch.tensor([fx, fy, cx, cy])
+            pyr.intrinsic_pyramid.append(prev if l == 0 else prev / (2 ** l))
+        pyr.depth, pyr.vmap, pyr.nmap, pyr.gray = (pyr.depth_pyramid[0], pyr.vertex_pyramid[0], pyr.normal_pyramid[0],
+                                                   pyr.intensity_pyramid[0])
+        return pyr

@@ -13,6 +13,7 @@
  *   egt_compute_gradients     gradient_kernel                TRK:853-926   (live: frame.py:72,97, system.py:92)
  *   egt_vertex_normal_map     compute_vertex/normal_map_kernel TRK:602-702 (live: frame.py:42, mapper.py:260)
  *   egt_solve_block           solveBlock (CPU Eigen QR)      TRK:929-950   (live: tracker.py:238)
+ *   egt_ingest_frame          Frame.__init__ + PyraImageCUDA (src/utils/frame.py:32-146) as one fused chain    
  *   egt_gn_accumulate         Tracker.tracking_optimization, first half (src/core/tracker.py:194-227): the PyTorch
  *                             functions projective_transform (src/core/optimizer.py:131-180), icp_optimization
  *                             (:317-377) and rgb_optimization (:278-315) fused into one pass        
@@ -95,6 +96,35 @@ EGS_API int egt_track_pyramid(const egt_level* levels, int32_t nlevel, const int
                               float dist_thres, int32_t use_rgb, float rgb_weight, float lm, float residual_thres,
                               float dx_thres, float* transform, double* sums, float* dx_out, float* system_out,
                               int32_t* status, void* stream);
+
+/* One level of a frame's pyramids as the tracker consumes them (PyraImageCUDA, src/utils/frame.py:22-99): row-major
+ * [height][width][C] float32 device arrays, caller-owned.  maskf is the float mask chain the reference keeps
+ * downsampling (frame.py:86); mask the bool map it derives per level (frame.py:69,88). */
+typedef struct egt_pyramid_level {
+    int32_t width, height;
+    float* depth;     /* [h][w]    bilateral-filtered depth (level 0: Frame.depth, frame.py:132; level l: frame.py:83-84) */
+    float* disp;      /* [h][w]    1 / (depth + 1e-6)                                  disp_pyramid */
+    uint8_t* mask;    /* [h][w]    (maskf > 0.9) & (depth > 0.1)                       mask_pyramid */
+    float* maskf;     /* [h][w]    float mask at this level */
+    float* vertex;    /* [h][w][3]                                                     vertex_pyramid */
+    float* normal;    /* [h][w][3]                                                     normal_pyramid */
+    float* gray;      /* [h][w]                                                        intensity_pyramid */
+    float* grad;      /* [h][w][3] d/dx, d/dy, sqrt(dx^2 + dy^2 + 1e-6)                grad_pyramid */
+} egt_pyramid_level;
+
+/*
+ * Frame ingest: everything Frame.__init__ + PyraImageCUDA compute on the device for one RGB-D
+ * frame (src/utils/frame.py:112-146, :32-99) as `nlevel` stream-ordered launches -- the 13x13 bilateral of the raw
+ * depth, vertex / normal map, grey image, derivatives and, per further level, the 5x5 stride-2 downsamples of grey /
+ * depth / mask / vertex / normal with the bilateral of the downsampled depth and the re-normalised normals.
+ * color [height][width][3] in 0..1, depth_raw [height][width] in metres (unfiltered), mask [height][width] float;
+ * levels[l] must be sized width >> l by height >> l.  Level l's intrinsics are (fx, fy, cx, cy) / 2^l ... the reference
+ * divides the PREVIOUS level's by 2^l (frame.py:80-81: level 2 = level 0 / 8); that list is host data and stays in
+ * the Python mirror (eggfusion_b200.tracking.ingest_frame).
+ */
+EGS_API int egt_ingest_frame(const float* color, const float* depth_raw, const float* mask, int32_t width, int32_t height,
+                             float fx, float fy, float cx, float cy, float sigma_color, float sigma_space, int32_t nlevel,
+                             const egt_pyramid_level* levels, void* stream);
 
 #ifdef __cplusplus
 }

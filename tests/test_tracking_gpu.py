@@ -112,3 +112,101 @@ def test_reference_python_wrappers_run_unchanged():
     assert torch.allclose(x, b / (2 + 1e-6), atol=1e-5)
     with pytest.raises(NotImplementedError):
         cuda_tracking.icp_optimization_cuda()
+
+
+# ---- fused frame ingest against the reference's own sequence --------------------------------------
+def _pyramid_sequence(ext, color, depth_raw, mask, intr, nlevel=3):
+    """Frame.__init__ + PyraImageCUDA._build_pyramid of the reference (src/utils/frame.py:112-146, :32-99) call for call,
+    through the extension module `ext` (its own build, or the per-function drop-in): the oracle of the fused chain."""
+    import torch.nn.functional as F
+
+    def call(fn, x, *shape_out, args=()):
+        o = torch.zeros(*shape_out, device=x.device)
+        fn(x, o, *args)
+        return o
+    H, W = depth_raw.shape[:2]
+    depth = call(ext.bilateral_filter_cuda, depth_raw, H, W, 1, args=(W, H, 13, 0.03, 4.5))            # frame.py:132
+    gray = (color[..., 0] * 0.114 + color[..., 1] * 0.587 + color[..., 2] * 0.299)[..., None]            # frame.py:40
+    fx, fy, cx, cy = intr
+    vmap, nmap = torch.zeros(H, W, 3, device=DEV), torch.zeros(H, W, 3, device=DEV)
+    ext.compute_vertex_and_normal_cuda(depth, fx, fy, cx, cy, vmap, nmap)                                 # frame.py:42
+    P = {k: [] for k in ("gray", "disp", "mask", "vertex", "normal", "grad", "depth")}
+
+    def grad_of(g):
+        h, w = g.shape[:2]
+        gx, gy = torch.zeros(h, w, device=DEV), torch.zeros(h, w, device=DEV)
+        ext.compute_gradients_cuda(g.contiguous(), gx, gy, w, h)
+        return torch.stack([gx, gy, torch.sqrt(gx ** 2 + gy ** 2 + 1e-6)], dim=-1).contiguous()
+
+    def down(x):
+        h, w, c = x.shape
+        o = torch.zeros(h // 2, w // 2, c, device=DEV)
+        ext.gaussian_downsample_cuda(x.contiguous().float(), o, w, h, c)
+        return o
+    m = mask
+    P["gray"].append(gray); P["vertex"].append(vmap); P["normal"].append(nmap); P["depth"].append(depth)
+    P["disp"].append(1.0 / (depth + 1e-6)); P["mask"].append((m > 0.9) & (depth > 0.1)); P["grad"].append(grad_of(gray))
+    for l in range(1, nlevel):                                                                            # frame.py:76-99
+        gray = down(gray)
+        depth = down(depth)
+        h, w = depth.shape[:2]
+        depth = call(ext.bilateral_filter_cuda, depth, h, w, 1, args=(w, h, 13, 0.03, 4.5))
+        m = down(m)
+        P["gray"].append(gray); P["depth"].append(depth); P["disp"].append(1.0 / (depth + 1e-6))
+        P["mask"].append((m > 0.9) & (depth > 0.1))
+        P["vertex"].append(down(P["vertex"][-1]))
+        P["normal"].append(F.normalize(down(P["normal"][-1]), dim=-1))
+        P["grad"].append(grad_of(gray))
+    return P
+
+
+def _ingest_inputs(W, H, seed=3):
+    rng = np.random.default_rng(seed)
+    v, u = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    depth = 1.6 + 0.4 * np.sin(u / 37.0) * np.cos(v / 23.0) + 0.003 * rng.normal(size=(H, W))
+    depth[(u > 0.6 * W) & (v < 0.3 * H)] += 0.7                # a depth edge
+    depth[rng.uniform(size=(H, W)) < 0.01] = 0.0               # sensor holes
+    color = np.stack([0.5 + 0.4 * np.sin(u / 9.0 + v / 13.0), 0.5 + 0.4 * np.cos(u / 7.0), 0.5 + 0.3 * np.sin(v / 5.0)], -1)
+    color += 0.02 * rng.normal(size=color.shape)
+    mask = (rng.uniform(size=(H, W)) > 0.02).astype(np.float32)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return _t(f32(np.clip(color, 0, 1))), _t(f32(depth)[..., None]), _t(mask[..., None])
+
+
+@pytest.mark.parametrize("W,H", [(161, 119), (640, 480), (1200, 680)])
+def test_fused_ingest_matches_the_per_function_sequence(W, H):
+    """egt_ingest_frame (3 launches) against the reference's call sequence through (a) the per-function drop-in kernels,
+    which are pinned on the reference's own kernels, and (b) the reference's own build when oracle/_ref travelled."""
+    from eggfusion_b200 import tracking as TRK
+    import cuda_tracking_ext as ours_ext
+    color, depth_raw, mask = _ingest_inputs(W, H)
+    intr = (0.5 * W, 0.5 * W, (W - 1) / 2.0, (H - 1) / 2.0)
+    pyr = TRK.FrameIngest(W, H, 3, device=DEV)(color, depth_raw, mask, intr)
+    exts = [("drop-in", ours_ext)]
+    mg = util._golden_mod()
+    ref_ext = mg.load_ref_tracking()
+    if ref_ext is not None:
+        exts.append(("reference", ref_ext))
+    got = {"gray": pyr.intensity_pyramid, "disp": pyr.disp_pyramid, "mask": pyr.mask_pyramid, "vertex": pyr.vertex_pyramid,
+           "normal": pyr.normal_pyramid, "grad": pyr.grad_pyramid, "depth": pyr.depth_pyramid}
+    for name, ext in exts:
+        want = _pyramid_sequence(ext, color, depth_raw, mask, intr)
+        torch.cuda.synchronize()
+        for l in range(3):
+            m_w, m_g = want["mask"][l], got["mask"][l]
+            # the bool mask thresholds depth > 0.1 and mask > 0.9: identical except where a value sits on the threshold
+            assert float((m_w != m_g).float().mean()) <= 1e-5, (name, l)
+            for k in ("gray", "depth", "vertex", "grad"):
+                a, b = got[k][l], want[k][l]
+                assert a.shape == b.shape, (name, k, l, a.shape, b.shape)
+                e = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+                assert e <= 2e-6, (name, k, l, e)
+            # disparity of sensor holes is 1/(0 + 1e-6): compare where the depth is valid
+            ok = want["depth"][l] > 0.05
+            e = float(((got["disp"][l] - want["disp"][l]).abs()[ok]).max() / want["disp"][l][ok].abs().max())
+            assert e <= 2e-6, (name, "disp", l, e)
+            nz_w, nz_g = (want["normal"][l] == 0).all(-1), (got["normal"][l] == 0).all(-1)
+            assert float((nz_w != nz_g).float().mean()) <= 1e-5, (name, "normal holes", l)
+            assert float((got["normal"][l] - want["normal"][l]).abs().max()) <= 2e-5, (name, "normal", l)
+    # the intrinsics list keeps the reference's quirk (level 2 = level 0 / 8, frame.py:80-81)
+    assert torch.allclose(pyr.intrinsic_pyramid[2], torch.tensor(intr) / 8.0)
