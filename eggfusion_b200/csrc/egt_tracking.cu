@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/eggtrack.h"
+#include "egt_qr.cuh"
 
 namespace {
 
@@ -156,41 +157,14 @@ __global__ void k_vertex_normal(const float* __restrict__ depth, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ small dense solve
-// (A + lm I) x = b by Gaussian elimination with partial pivoting in fp64, one thread: n <= 16 is 6 in practice
-// (9 solves per frame); this removes the reference's GPU -> CPU (Eigen QR) -> GPU round trip.
+// (A + lm I) x = b by the reference's own algorithm -- Eigen's column-pivoted Householder QR in fp32 on the column-major
+// view of the buffer (egt_qr.cuh) -- but on the device, one thread: n <= 16 is 6 in practice (9 solves per frame); this
+// removes the reference's GPU -> CPU (Eigen) -> GPU round trip and keeps its behaviour on non-symmetric and
+// rank-deficient systems (basic solution, zeros for the dropped pivots).
 __global__ void k_solve_block(const float* __restrict__ A, const float* __restrict__ b, float lm, float* __restrict__ x,
                               int n) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double M[16][17];
-    for (int r = 0; r < n; r++) {
-        for (int c = 0; c < n; c++) M[r][c] = (double)A[r * n + c] + (r == c ? (double)lm : 0.0);
-        M[r][n] = (double)b[r];
-    }
-    bool singular = false;
-    for (int k = 0; k < n; k++) {
-        int p = k;
-        double best = fabs(M[k][k]);
-        for (int r = k + 1; r < n; r++)
-            if (fabs(M[r][k]) > best) { best = fabs(M[r][k]); p = r; }
-        if (!(best > 0.0)) { singular = true; break; }
-        if (p != k)
-            for (int c = k; c <= n; c++) { const double t = M[k][c]; M[k][c] = M[p][c]; M[p][c] = t; }
-        for (int r = k + 1; r < n; r++) {
-            const double f = M[r][k] / M[k][k];
-            for (int c = k; c <= n; c++) M[r][c] -= f * M[k][c];
-        }
-    }
-    if (singular) {
-        for (int r = 0; r < n; r++) x[r] = 0.f;
-        return;
-    }
-    double sol[16];
-    for (int r = n - 1; r >= 0; r--) {
-        double s = M[r][n];
-        for (int c = r + 1; c < n; c++) s -= M[r][c] * sol[c];
-        sol[r] = s / M[r][r];
-    }
-    for (int r = 0; r < n; r++) x[r] = (float)sol[r];
+    egt_colpiv_qr_solve(A, b, lm, x, n);
 }
 
 inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }

@@ -53,8 +53,10 @@ EGS_API int egt_compute_gradients(const float* in, float* grad_x, float* grad_y,
 EGS_API int egt_vertex_normal_map(const float* depth, float fx, float fy, float cx, float cy, float* vertex_map,
                                   float* normal_map, int32_t width, int32_t height, void* stream);
 
-/* x = solve((A + lm I) x = b) for one dense n x n system, n <= 16, entirely on the device (A row- or column-major:
- * the tracker's A is symmetric).  Singular systems yield zeros. */
+/* x = (A' + lm I).colPivHouseholderQr().solve(b) for one dense n x n system, n <= 16, entirely on the device: the
+ * reference's algorithm (Eigen's column-pivoted Householder QR, fp32) on the reference's view of the buffer (A' = the
+ * n x n buffer read COLUMN-major, i.e. the transpose of torch's row-major matrix; the tracker's A is symmetric).
+ * Rank-deficient systems get Eigen's basic solution (zeros for the dropped pivots). */
 EGS_API int egt_solve_block(const float* A, const float* b, float lm, float* x, int32_t n, void* stream);
 
 /* One pyramid level of the model (rendered, "prev"/frame1) and of the incoming frame ("curr"/frame2), PyraImageCUDA

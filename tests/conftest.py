@@ -37,7 +37,8 @@ def hostemu():
     deps = [src, os.path.join(ROOT, "eggfusion_b200", "csrc", "egs_surfel_math.cuh"),
             os.path.join(ROOT, "eggfusion_b200", "csrc", "egs_common.cuh"),
             os.path.join(ROOT, "eggfusion_b200", "csrc", "egm_math.cuh"),
-            os.path.join(ROOT, "eggfusion_b200", "csrc", "egt_gn_math.cuh")]
+            os.path.join(ROOT, "eggfusion_b200", "csrc", "egt_gn_math.cuh"),
+            os.path.join(ROOT, "eggfusion_b200", "csrc", "egt_qr.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.run([cxx, "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-I/usr/local/cuda/include", "-shared",

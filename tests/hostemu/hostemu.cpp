@@ -4,6 +4,7 @@
 #include "../../eggfusion_b200/csrc/egs_surfel_math.cuh"
 #include "../../eggfusion_b200/csrc/egm_math.cuh"
 #include "../../eggfusion_b200/csrc/egt_gn_math.cuh"
+#include "../../eggfusion_b200/csrc/egt_qr.cuh"
 #include <cmath>
 #include <cstring>
 
@@ -23,6 +24,11 @@ static FrameConst make_fc(int W, int H, int D, int M, float tanfovx, float tanfo
 }
 
 extern "C" {
+
+// the product's 6x6 solve (egt_solve_block) on the CPU
+int emu_colpiv_qr_solve(const float* A, const float* b, float lm, float* x, int n) {
+    return egt_colpiv_qr_solve(A, b, lm, x, n);
+}
 
 void emu_surfel_forward(int P, int W, int H, int D, int M, float tanfovx, float tanfovy, float cx, float cy, float mod,
                         const float* view, const float* proj, const float* campos, const float* bg, const float* means,

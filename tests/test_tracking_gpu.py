@@ -77,20 +77,41 @@ def test_tracking_utils_match_reference_golden():
 
 
 def test_solve_block_on_device():
+    """egt_solve_block = the reference's solveBlock (Eigen colPivHouseholderQr, fp32, column-major view; tracking.cu:929-950)
+    on the device, against the restatement of that algorithm (oracle/qr_oracle.py): well-conditioned, ill-conditioned,
+    non-symmetric and rank-deficient systems."""
     import cuda_tracking_ext as ext
+    from oracle.qr_oracle import colpiv_householder_qr_solve as qr_solve
     rng = np.random.default_rng(4)
+    eps = np.finfo(np.float32).eps
+    cases = []
     for n in (6, 3, 12):
         J = rng.normal(size=(200, n))
-        A = (J.T @ J).astype(np.float32)
-        b = rng.normal(size=(n, 1)).astype(np.float32)
+        cases.append(((J.T @ J).astype(np.float32), rng.normal(size=n).astype(np.float32), 1.0e-6))
+    for p in (2, 4, 6):                                            # ill-conditioned Gauss-Newton matrices
+        J = rng.normal(size=(80, 6)) * np.array([1, 1, 10.0 ** p, 1, 10.0 ** (-p / 2), 1])
+        cases.append(((J.T @ J).astype(np.float32), rng.normal(size=6).astype(np.float32), 1.0e-6))
+    cases.append((rng.normal(size=(6, 6)).astype(np.float32), rng.normal(size=6).astype(np.float32), 0.0))   # non-symmetric
+    B = rng.normal(size=(4, 6))
+    A4 = (B.T @ B).astype(np.float32)
+    cases.append((A4, (A4 @ rng.normal(size=6)).astype(np.float32), 0.0))                                    # rank 4
+    for A, b, lm in cases:
+        n = A.shape[0]
         x = torch.zeros(n, 1, device=DEV)
-        ext.solve_block_cuda(_t(A), _t(b), 1.0e-6, x)
-        want = orc.solve_block(A, b, 1.0e-6)
-        assert rel_err(x.cpu().numpy().reshape(-1), want) <= 1e-4
-    # singular system -> zeros, no NaN
+        ext.solve_block_cuda(_t(A), _t(b.reshape(n, 1)), lm, x)
+        got = x.cpu().numpy().reshape(-1)
+        want, rank = qr_solve(A, b, lm)
+        assert np.array_equal(got == 0, want == 0), (n, rank)                     # same pivots dropped
+        M = A.T.astype(np.float64) + lm * np.eye(n)
+        cond = min(np.linalg.cond(M), 1e7) if rank == n else 1e4
+        assert np.abs(got - want).max() <= 20 * eps * cond * np.abs(want).max() + 1e-7, (n, rank, cond)
+        if rank == n and cond < 1e5:                                              # and both solve the system
+            x64 = np.linalg.solve(M, b.astype(np.float64))
+            assert rel_err(got, x64) <= 1e-3
+    # the damped zero system the tracker can produce when no pixel is valid: (0 + lm I) x = b
     x = torch.ones(6, 1, device=DEV)
-    ext.solve_block_cuda(torch.zeros(6, 6, device=DEV), torch.ones(6, 1, device=DEV), 0.0, x)
-    assert float(x.abs().max()) == 0.0
+    ext.solve_block_cuda(torch.zeros(6, 6, device=DEV), torch.ones(6, 1, device=DEV), 1.0e-6, x)
+    assert torch.allclose(x, torch.full_like(x, 1.0e6), rtol=1e-5)
 
 
 def test_reference_python_wrappers_run_unchanged():
