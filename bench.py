@@ -657,13 +657,63 @@ def run_ours(args):
         for i in range(args.warmup):
             one_step(i, False)
         barrier()
+        graphs = None
+        if world > 1 and not args.no_graph:
+            # N > 1: a rank's share of the step is ~0.1 ms of GPU work per stage, less than Python needs to enqueue it, so
+            # the steady-state step is recorded ONCE (one CUDA graph per camera cycle: 4 steps, even, so the exchange's
+            # inbox parity is back where it started) and replayed; K % 4 trailing steps get their own graph.
+            try:
+                cyc = len(settings)
+                assert cyc % 2 == 0
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for i in range(cyc):
+                        one_step(i, False)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                g_cyc = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_cyc):
+                    for i in range(cyc):
+                        one_step(i, False)
+                g_rem, rem = None, args.steps % cyc
+                if rem:
+                    g_rem = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_rem):
+                        for i in range(rem):
+                            one_step(i, False)
+                graphs = (g_cyc, g_rem, cyc, rem)
+                for _ in range(2):
+                    g_cyc.replay()
+                barrier()
+            except Exception as ex:
+                if rank == 0:
+                    print("bench: CUDA-graph capture of the sharded step failed (%s); timing eager launches" % (ex,),
+                          file=sys.stderr)
+                graphs = None
+                barrier()
         sampler = ClockSampler(local)
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        used = [one_step(i, True) for i in range(args.steps)]
-        ev1.record()
-        barrier()
+        if graphs is None:
+            ev0.record()
+            used = [one_step(i, True) for i in range(args.steps)]
+            ev1.record()
+            barrier()
+        else:
+            g_cyc, g_rem, cyc, rem = graphs
+            ev0.record()
+            for _ in range(args.steps // cyc):
+                g_cyc.replay()
+            if g_rem is not None:
+                g_rem.replay()
+            ev1.record()
+            barrier()
+            used = [i % cyc for i in range(args.steps)]
+            # per-stage breakdown: an eager pass over the same kernels with CUDA events between the stages (its total is
+            # launch-bound at large N and is NOT what `value` reports)
+            for i in range(min(args.steps, 24)):
+                one_step(i, True)
+            barrier()
         clocks = sampler.stop()
         ms_total = ev0.elapsed_time(ev1)
         counters = ctx.read_counters()
@@ -692,11 +742,13 @@ def run_ours(args):
         return dict(scene=scene, cams=cams, grads=grads, deg=deg, P=P, M=M, W=W, H=H, params=params, bg=bg,
                     settings=settings, mask=mask, costs=costs, cap=cap, stage_ms=stage_ms, I_mean=I_mean,
                     vis_mean=vis_mean, ms_step=ms_step, I_total=I_total, clocks=clocks, exchange=exch,
+                    graphed=graphs is not None,
                     I_all_cams=I_all,
                     value=256.0 * I_total / (ms_step * 1e-3) / 1e6)
 
     main_run = device_resident(args.workload)
     exchange_kind = main_run["exchange"] is not None
+    graphed_run = main_run["graphed"]
     scene, cams, grads, deg = main_run["scene"], main_run["cams"], main_run["grads"], main_run["deg"]
     P, M, W, H, params, bg = (main_run[k] for k in ("P", "M", "W", "H", "params", "bg"))
     settings, mask, cap = main_run["settings"], main_run["mask"], main_run["cap"]
@@ -965,6 +1017,8 @@ def run_ours(args):
         line["exchange"] = ("nvlink peer memory (egs_push_rows: the touched rows stored into the owners' inboxes, device "
                             "barrier, egs_fold_inbox)") if exchange_kind else "nccl reduce_scatter_tensor"
         line["tile_partition"] = "round-robin tile rows" if args.round_robin else "tile rows balanced by list length"
+        line["launch"] = ("the sharded step recorded once per camera cycle into a CUDA graph and replayed (stage_ms: a separate "
+                          "eager pass with events)") if graphed_run else "eager launches"
         line["c4"] = c4
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sample(scene, cams, grads, deg)

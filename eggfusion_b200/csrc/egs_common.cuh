@@ -2,7 +2,7 @@
 //
 // HBM layout (all caller-owned, see include/eggsplat.h):
 //   geom workspace, per surfel:   SplatRecord rec[P] (64 B, 16-B aligned quads) | cov3D[P][6] f32 |
-//                                 tiles_touched[P] u32 | clamped[P] u8
+//                                 tiles_touched[P] u32 | clamped[P] u8 | cand[P] i32 (sharded projection's candidate list)
 //   img  workspace:               egs_counters (+ticket) | tile_count[T] | tile_offset[T+1] | tile_cursor[T] |
 //                                 tile_list[T] (compacted non-empty tiles) | hit_count[8T] | final_T[N] | final_D[N] |
 //                                 n_contrib[N]
@@ -87,6 +87,7 @@ struct GeomView {
     float* cov3D;
     uint32_t* tiles_touched;
     uint8_t* clamped;
+    int32_t* cand;          // [P] sharded projection: ids of the surfels that may reach the rank's tiles (egs_preprocess.cu)
     size_t bytes;
 };
 struct ImgView {
@@ -118,6 +119,7 @@ EGS_HD GeomView carve_geom(void* base, size_t P) {
     v.cov3D = (float*)(b + o);              o = egs_align_up(o + sizeof(float) * 6 * P, 256);
     v.tiles_touched = (uint32_t*)(b + o);   o = egs_align_up(o + sizeof(uint32_t) * P, 256);
     v.clamped = (uint8_t*)(b + o);          o = egs_align_up(o + P, 256);
+    v.cand = (int32_t*)(b + o);             o = egs_align_up(o + sizeof(int32_t) * P, 256);
     v.bytes = o + 256;
     return v;
 }

@@ -30,6 +30,66 @@ __device__ __forceinline__ void unstage_sh_rows(const float* s_sh, float* __rest
 #define SH_BULK_PITCH 52   // floats per row for the bulk-copied layout: 208-B rows keep 16-B alignment and make the
                            // per-thread LDS.128 of a quarter-warp conflict-free (52 mod 32 = 20 -> 8 distinct 4-bank groups)
 
+// Sharded frames only: can this surfel reach one of the rank's tiles at all?  A cheap, conservative answer from the
+// projected centre and an upper bound of the splat radius -- lambda_max(cov2D) <= |J|_F^2 (mod max(sx, sy))^2 + 0.3, and
+// the reference's radius formula never exceeds 3 sqrt(2 lambda_max + 0.32) (its max(0.1, .) floor) -- so that the ~1500
+// instructions of the exact projection are spent only on the ~1/world of the surfels that can matter to this rank.
+__device__ __forceinline__ bool surfel_misses_mask(const FrameConst& fc, const float* mean, const float* scale,
+                                                   const int32_t* __restrict__ tile_mask) {
+    const float px = mean[0], py = mean[1], pz = mean[2];
+    const float hw = xf_affine(fc.proj, 3, px, py, pz);
+    const float vz = xf_affine(fc.view, 2, px, py, pz);
+    if (!(vz > 0.05f) || !(hw > 0.05f)) return false;    // near / behind the camera: leave it to the exact path
+    const float pw = 1.0f / (hw + 0.0000001f);
+    const float ix = xf_affine(fc.proj, 0, px, py, pz) * pw * (float)fc.W * 0.5f + fc.cx;
+    const float iy = xf_affine(fc.proj, 1, px, py, pz) * pw * (float)fc.H * 0.5f + fc.cy;
+    const float smax = fc.mod * fmaxf(fabsf(scale[0]), fabsf(scale[1]));
+    const float lx = 1.3f * fc.tanfovx, ly = 1.3f * fc.tanfovy, iz = 1.0f / vz;
+    const float jf = (fc.fx * iz) * (fc.fx * iz) * (1.f + lx * lx) + (fc.fy * iz) * (fc.fy * iz) * (1.f + ly * ly);
+    const float lam = smax * smax * jf + 0.3f;
+    const float rad = ceilf(3.f * sqrtf(2.f * lam + 0.32f) * 1.001f) + 2.f;   // + 2 px: the centre above is not the exact one
+    if (!(rad < 16384.f)) return false;
+    int x0, y0, x1, y1;
+    egs_tile_rect(ix, iy, (int)rad, fc.gx, fc.gy, x0, y0, x1, y1);
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++)
+            if (__ldg(tile_mask + y * fc.gx + x) != 0) return false;
+    return true;
+}
+
+// Pass 1 of a sharded projection: surfels that cannot reach the rank's tiles (and are not owned) get zero radii /
+// active / tiles_touched here and are never looked at again; the others are compacted into `cand` (warp-aggregated
+// append, order irrelevant) so that the exact projection runs on dense warps.  Surfel order carries no spatial
+// coherence, so skipping inside the projection kernel itself saves nothing (a warp always contains a surfel that
+// needs the full path: measured, 0.110 -> 0.158 ms at 2 ranks).
+__global__ void __launch_bounds__(256)
+k_surfel_candidates(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
+                    const int32_t* __restrict__ tile_mask, int own_first, int own_count, int32_t* __restrict__ radii,
+                    uint8_t* __restrict__ active, uint32_t* __restrict__ tiles_touched, int32_t* __restrict__ cand,
+                    int32_t* __restrict__ cand_count) {
+    __shared__ FrameConst fc;
+    load_frame_const(fc, f);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < f.num_surfels) {
+        keep = (i >= own_first && i - own_first < own_count) ||
+               !surfel_misses_mask(fc, means + (size_t)3 * i, scales + (size_t)3 * i, tile_mask);
+        if (!keep) {
+            radii[i] = 0;
+            active[i] = 0;
+            tiles_touched[i] = 0u;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(cand_count, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (keep) cand[base + __popc(bal & ((1u << lane) - 1u))] = i;
+}
+
 // SH_SMEM = 1: the CTA's SH block (M == 16: 128 x 192 B, contiguous) is staged through shared memory with fully
 // coalesced 16-byte loads and read on demand, instead of living in 48 registers per thread.
 // SH_SMEM = 2: every thread issues ONE 192-byte bulk copy (cp.async.bulk -> mbarrier, the TMA engine) of its SH row at
@@ -40,7 +100,8 @@ __global__ void __launch_bounds__(SURF_THREADS)
 k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ opac, const float* __restrict__ shs,
                  const float* __restrict__ colors, const int32_t* __restrict__ tile_mask, GeomView g, ImgView im,
-                 int32_t* __restrict__ radii, uint8_t* __restrict__ active, int own_first, int own_count) {
+                 int32_t* __restrict__ radii, uint8_t* __restrict__ active, int own_first, int own_count,
+                 const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_count) {
     // own_first / own_count: the surfel range this rank owns in a tile-sharded frame.  A visible surfel whose
     // rectangle has no tile in the rank's mask and which lies outside the range is needed by nobody here: its colour
     // (SH evaluation, 192 B of coefficients) and its record / cov3D / clamp state are skipped.  SH_SMEM == 3 is the
@@ -49,7 +110,12 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
     __shared__ __align__(128) float s_sh[SH_SMEM >= 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
     __shared__ __align__(8) unsigned long long s_bar;
     load_frame_const(fc, f);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // cand != nullptr (sharded frames at >= 3 ranks): thread j works on surfel cand[j], j < *cand_count -- the surfels a
+    // cheap footprint bound could not rule out (k_surfel_candidates); everything else was zeroed there
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_work = cand ? *cand_count : f.num_surfels;
+    if (cand && blockIdx.x * blockDim.x >= n_work) return;      // whole CTA beyond the list (uniform)
+    const int i = cand ? (j < n_work ? cand[j] : f.num_surfels) : j;
     const uint32_t bar = smem_addr(&s_bar);
     if (SH_SMEM == 1) {
         const int row0 = blockIdx.x * SURF_THREADS;
@@ -325,18 +391,32 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
         sh_bulk = (e && e[0] == 'l') ? 0 : 1;
     }
     const bool sharded = tile_mask != nullptr && own_count < P;   // most SH rows will not be needed: fetch on demand
-    if (sh_smem && sharded)
-        k_surfel_forward<3><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
-                                                            radii, active, own_first, own_count);
-    else if (sh_smem && sh_bulk)
+    if (sh_smem && sharded) {
+        // two passes when the rank owns a third of the surfels or less (>= 3 ranks): candidate compaction
+        // (k_surfel_candidates), then the exact projection on the candidates only, on dense warps
+        static int two_pass = -1;
+        if (two_pass < 0) {
+            const char* e = getenv("EGS_SHARD_TWO_PASS");   // "0": never, "1": always (tests), default: own_count <= P / 3
+            two_pass = e ? (e[0] == '1' ? 1 : 0) : 2;
+        }
+        if (two_pass == 1 || (two_pass == 2 && (long long)own_count * 3 <= (long long)P)) {
+            int32_t* cand_count = reinterpret_cast<int32_t*>(im.ticket);   // zeroed by the plan's head memset
+            k_surfel_candidates<<<(P + 255) / 256, 256, 0, s>>>(f, means, scales, tile_mask, own_first, own_count, radii,
+                                                                active, g.tiles_touched, g.cand, cand_count);
+            k_surfel_forward<3><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
+                                                                im, radii, active, own_first, own_count, g.cand, cand_count);
+        } else
+            k_surfel_forward<3><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
+                                                                im, radii, active, own_first, own_count, nullptr, nullptr);
+    } else if (sh_smem && sh_bulk)
         k_surfel_forward<2><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
-                                                            radii, active, own_first, own_count);
+                                                            radii, active, own_first, own_count, nullptr, nullptr);
     else if (sh_smem)
         k_surfel_forward<1><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g, im,
-                                                            radii, active, own_first, own_count);
+                                                            radii, active, own_first, own_count, nullptr, nullptr);
     else
         k_surfel_forward<0><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
-                                                                im, radii, active, own_first, own_count);
+                                                                im, radii, active, own_first, own_count, nullptr, nullptr);
     return cudaGetLastError();
 }
 

@@ -268,7 +268,10 @@ class FrameBatchOptimizer:
 
 class FusedMapper:
     """One mapping iteration = 4 C-ABI stages on persistent buffers (SplatContext) + 2 glue stages, no autograd, no
-    allocation, no host sync.  `iterate()` returns the device tensor [total, color, depth, normal, reg]."""
+    allocation, no host sync.  `iterate()` returns the device tensor [total, color, depth, normal, reg].
+    Capacity overflow (more (tile, surfel) instances than the fixed binning workspace holds) is watched without a sync:
+    every frame's counters follow the render to pinned host memory and the NEXT iterate() (or synchronize()) raises if
+    one of them carried the overflow flag."""
 
     def __init__(self, opt: FrameBatchOptimizer, width: int, height: int, capacity: int, sh_degree: int):
         self.opt = opt
@@ -282,9 +285,10 @@ class FusedMapper:
 
     def iterate(self, settings, frame_input, render_mask, mark=None):
         o, ctx = self.opt, self.ctx
+        ctx.check_overflow()
         ctx.set_camera(settings)
         with torch.no_grad():
-            ctx.forward(o.xyz, o.shs, None, o.opacity, o.scales, o.rotations, None, mark)
+            ctx.forward(o.xyz, o.shs, None, o.opacity, o.scales, o.rotations, None, mark, watch_overflow=True)
             loss_seed(ctx.color, ctx.depth, ctx.normal, frame_input["color_map"], frame_input.get("depth_map"),
                       frame_input.get("normal_map_c"), render_mask[0], render_mask[1], o.weights,
                       out=(self.terms, self.g_color, self.g_depth, self.g_normal))
@@ -298,3 +302,8 @@ class FusedMapper:
                 mark("adam")
             return o.loss_values(self.terms, frame_input.get("depth_map") is not None,
                                  frame_input.get("normal_map_c") is not None)
+
+    def synchronize(self) -> None:
+        """Waits for the iterations issued so far and raises if any of them overflowed the binning capacity."""
+        torch.cuda.synchronize(self.opt.device)
+        self.ctx.check_overflow(block=True)

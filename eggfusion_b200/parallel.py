@@ -400,9 +400,10 @@ class DistributedMapper:
     def iterate(self, settings, frame_input, render_mask):
         from . import _lib, mapping as MP, rasterizer as R
         o, ctx = self.opt, self.ctx
+        ctx.check_overflow()      # a previous frame of THIS rank's shard overflowed the binning capacity -> raise here
         ctx.set_camera(settings)
         with torch.no_grad():
-            ctx.forward(o.xyz, o.shs, None, o.opacity, o.scales, o.rotations, self.tile_mask)
+            ctx.forward(o.xyz, o.shs, None, o.opacity, o.scales, o.rotations, self.tile_mask, watch_overflow=True)
             MP.loss_seed(ctx.color, ctx.depth, ctx.normal, frame_input["color_map"], frame_input.get("depth_map"),
                          frame_input.get("normal_map_c"), render_mask[0], render_mask[1], o.weights,
                          out=(self.terms, self.g_color, self.g_depth, self.g_normal), tile_mask=self.tile_mask)
@@ -436,3 +437,8 @@ class DistributedMapper:
                     self._all_gather_rows(name)
             return o.loss_values(self.terms, frame_input.get("depth_map") is not None,
                                  frame_input.get("normal_map_c") is not None)
+
+    def synchronize(self) -> None:
+        """Waits for the iterations issued so far and raises if any of this rank's frames overflowed its capacity."""
+        torch.cuda.synchronize(self.opt.device)
+        self.ctx.check_overflow(block=True)

@@ -49,6 +49,7 @@ class SplatContext:
             self.counters_host = torch.zeros((4,), dtype=torch.int32).pin_memory()
         self.frame = None
         self._keep = None
+        self._watch = []        # (event, pinned counters) of forwards whose overflow flag has not been looked at yet
         self.own_range = (0, self.P) if own_range is None else (int(own_range[0]), int(own_range[1]))
 
     def set_camera(self, settings) -> None:
@@ -56,10 +57,18 @@ class SplatContext:
 
     # each stage is one C-ABI call; `mark(stage_name)` (optional) is invoked after each for event timing
     def forward(self, means3D, shs, colors_precomp, opacities, scales, rotations, tile_mask=None,
-                mark: Optional[Callable[[str], None]] = None, fetch_counters: bool = False, save: bool = True) -> None:
+                mark: Optional[Callable[[str], None]] = None, fetch_counters: bool = False, save: bool = True,
+                watch_overflow: bool = False) -> None:
+        """watch_overflow: the frame's counters travel to a pinned host buffer behind the render (asynchronously, no
+        sync) and `check_overflow()` raises once they have arrived with the overflow flag set -- the fixed-capacity
+        binning workspace truncated the instance lists, so images and gradients of that frame are wrong.  Not available
+        while the stream is being captured into a CUDA graph (read_counters() after the replay instead)."""
         lib, fr = self.lib, self.frame
         stream = R._stream_ptr(self.device)
         tm = None if tile_mask is None else tile_mask.data_ptr()
+        watch = None
+        if watch_overflow and not R._capturing():
+            watch = R._get_pinned()
         with torch.cuda.device(self.device):
             _lib.check(lib.egs_forward_plan_sharded(C.byref(fr), means3D.data_ptr(), R._ptr(shs), R._ptr(colors_precomp),
                                                     opacities.data_ptr(), scales.data_ptr(), rotations.data_ptr(), tm,
@@ -72,11 +81,34 @@ class SplatContext:
             _lib.check(lib.egs_forward_render(C.byref(fr), tm, self.radii.data_ptr(), self.geom.data_ptr(),
                                               self.img.data_ptr(), self.bin.data_ptr(), self.cap, self.color.data_ptr(),
                                               self.normal.data_ptr(), self.depth.data_ptr(), self.opacity.data_ptr(),
-                                              self.counters_host.data_ptr() if fetch_counters else None,
+                                              watch.data_ptr() if watch is not None else
+                                              (self.counters_host.data_ptr() if fetch_counters else None),
                                               0 if save else _lib.EGS_FWD_NO_SAVE, stream),
                        "forward_render")
+            if watch is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._watch.append((ev, watch))
         if mark:
             mark("render")
+
+    def check_overflow(self, block: bool = False) -> None:
+        """Raises if a watched forward (forward(watch_overflow=True)) overflowed the binning capacity.  Non-blocking by
+        default: only counters that have already arrived are examined; block=True waits for all of them."""
+        while self._watch:
+            ev, host = self._watch[0]
+            if not block and not ev.query():
+                return
+            ev.synchronize()
+            self._watch.pop(0)
+            n, flag = int(host[0]), int(host[2])
+            R._pinned_free.append(host)
+            if flag != 0:
+                self._watch.clear()
+                raise RuntimeError(
+                    f"eggsplat: a frame produced {n} (tile, surfel) instances but this SplatContext's binning workspace "
+                    f"holds {self.cap}; its lists were truncated and that frame's images / gradients are wrong. "
+                    f"Build the context (FusedMapper / DistributedMapper) with a larger capacity.")
 
     def backward_render(self, g_color, g_normal, g_depth, g_opac, mark=None, prezeroed: bool = False) -> None:
         """prezeroed: the screen-gradient block is known to be all zeros already (the peer exchange of a sharded step

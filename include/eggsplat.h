@@ -111,10 +111,12 @@ EGS_API int egs_forward_plan(const egs_frame* frame, const float* means3D, const
 /*
  * egs_forward_plan for one rank of a tile-sharded frame (the seam is the reference's tile_mask,
  * forward.cu:292-300, rasterizer_impl.cu:103-111).  The rank renders the tiles of `tile_mask` and owns the surfels
- * [own_first, own_first + own_count) for the per-surfel backward.  radii / active_mask / tiles_touched are written for
- * every surfel as usual, but the colour (SH evaluation), the splat record and the per-surfel backward state of a
- * visible surfel are produced only if it touches one of the rank's tiles or lies in the owned range -- nobody on this
- * rank reads them otherwise.  egs_forward_plan == own range [0, P).
+ * [own_first, own_first + own_count) for the per-surfel backward.  The colour (SH evaluation), the splat record and the
+ * per-surfel backward state of a visible surfel are produced only if it touches one of the rank's tiles or lies in the
+ * owned range -- nobody on this rank reads them otherwise -- and a surfel that a cheap conservative bound of its
+ * footprint places outside all of the rank's tiles (and outside the owned range) is not projected at all: its radii /
+ * active_mask entries are 0 on THIS rank (the union over the ranks is the single-GPU result).
+ * egs_forward_plan == own range [0, P): every entry exact.
  */
 EGS_API int egs_forward_plan_sharded(const egs_frame* frame, const float* means3D, const float* shs,
                                      const float* colors_precomp, const float* opacities, const float* scales,

@@ -181,6 +181,19 @@ def test_autograd_level_equals_fused_mapper():
     fm = M.FusedMapper(opt_b, W, H, capacity=200000, sh_degree=deg)
     losses_b = [n(fm.iterate(settings, frame, masks)).copy() for _ in range(2)]
     assert fm.ctx.read_counters()[2] == 0
+    fm.synchronize()                       # no overflow: does not raise
+    # a mapper whose binning workspace is too small says so (at the next iterate / synchronize), instead of silently
+    # optimising on truncated instance lists
+    small = M.FusedMapper(M.FrameBatchOptimizer({k: t(v) for k, v in raw.items()}, lr, w), W, H, capacity=64,
+                          sh_degree=deg)
+    small.iterate(settings, frame, masks)
+    with pytest.raises(RuntimeError, match="binning workspace"):
+        small.synchronize()
+    small.iterate(settings, frame, masks)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="binning workspace"):
+        small.iterate(settings, frame, masks)
+    small.ctx._watch.clear()
     for i in range(2):
         image_b = losses_b[i][0] - w.reg_weight * losses_b[i][4]
         assert abs(image_b - losses_a[i]) <= 1e-5 * abs(losses_a[i])

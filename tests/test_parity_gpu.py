@@ -199,6 +199,51 @@ def test_dropin_autograd_api_matches_raw():
         assert rel_err(leaf[k].grad.cpu().numpy(), raw[gk]) <= 1e-5, k   # atomics order only
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_projection_equals_the_full_one_on_the_ranks_tiles(world):
+    """One rank's view of a tile-sharded frame (egs_forward_plan_sharded; at >= 3 ranks the two-pass projection with the
+    candidate list): the rank's pixels are bit-identical to the un-sharded frame's, radii / active_mask agree on every
+    surfel the rank keeps, and every dropped surfel indeed reaches none of the rank's tiles and is not owned.  Backward
+    over the rank's pixels: the owned rows equal the same backward of the un-sharded plan."""
+    import eggfusion_b200 as E
+    from eggfusion_b200 import parallel as par, rasterizer as R, synthetic as syn
+    P, W, H, L, deg = syn.CONFIGS["C2"]
+    cam = syn.default_camera(W, H, syn.look_from((0.03, -0.02, 0.02), 0.02, -0.01))
+    sc = syn.make_scene(P, syn.default_camera(W, H), layers=L, sh_degree=deg)
+    g = syn.make_pixel_grads(cam, with_opacity=True)
+    s = _settings(E, cam, np.zeros(3, np.float32), deg)
+    empty = torch.Tensor([])
+    means, shs, opac = _t(sc["xyz"]), _t(sc["shs"]), _t(sc["opacity"])
+    scales, rots = _t(sc["scales"]), _t(sc["rotations"])
+    ty, tx = (H + 15) // 16, (W + 15) // 16
+    rank = world - 1
+    mask = par.tile_partition(ty, tx, world, rank).to(DEV)
+    first, count = par.surfel_range(P, world, rank)
+    full = R.forward_raw(s, means, shs, empty, opac, scales, rots, mask)
+    shard = R.forward_raw(s, means, shs, empty, opac, scales, rots, mask, own_range=(first, count))
+    for a, b in zip(shard[:4], full[:4]):
+        assert torch.equal(a, b)
+    assert shard[6].num_rendered == full[6].num_rendered
+    kept = shard[5] > 0
+    assert torch.equal(shard[5][kept], full[5][kept]) and torch.equal(shard[4][kept], full[4][kept])
+    dropped = (~kept) & (full[5] > 0)
+    assert int(dropped.sum()) > 0 or world < 3        # below 3 ranks the single-pass projection keeps every radius
+    idx = torch.nonzero(dropped).flatten()
+    assert not bool(((idx >= first) & (idx < first + count)).any())
+    # a dropped surfel's exact tile rectangle holds no tile of the rank: the un-sharded plan emitted no instance for it
+    pl = full[6].point_list() if hasattr(full[6], "point_list") else None
+    if pl is not None:
+        assert not bool(torch.isin(pl.long(), idx).any())
+    gt = [_t(g[k]) for k in ("color", "normal", "depth", "opacity")]
+    px = mask.repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W].float()
+    gt = [t * px for t in gt]
+    g_full = R.backward_raw(full[6], means, shs, empty, scales, rots, *gt)
+    g_shard = R.backward_raw(shard[6], means, shs, empty, scales, rots, *gt)
+    for k in ("means3D", "opacities", "sh", "scales", "rotations"):
+        a, b = g_shard[k].reshape(P, -1)[first:first + count], g_full[k].reshape(P, -1)[first:first + count]
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max() + 1e-30), k
+
+
 def test_colors_precomp_path():
     import eggfusion_b200 as E
     from eggfusion_b200 import rasterizer as R
