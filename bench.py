@@ -601,7 +601,7 @@ def run_ours(args):
                 rg = R.debug_export(out[6], P, W, H)["ranges"].double()
                 costs += rg[:, 1] - rg[:, 0]
                 del out, rg
-            mask = par.tile_partition(ty, tx, world, rank, None if args.round_robin else costs).to(dev)
+            mask = par.tile_partition(ty, tx, world, rank, None if args.round_robin else costs, args.partition).to(dev)
         # instance counts per camera (exact mode, outside the timed region) -> capacity of the persistent context
         I_cam, vis_cam = [], []
         for s in settings:
@@ -779,7 +779,7 @@ def run_ours(args):
         s_static = E.GaussianRasterizationSettings(H, W, c0.tanfovx, c0.tanfovy, bg, 1.0, st_view, st_proj, deg, st_campos,
                                                    False, False, c0.cx, c0.cy)
 
-        sharder = par.ShardedSplat(costs=None if args.round_robin else main_run["costs"]) if world > 1 else None
+        sharder = par.ShardedSplat(costs=None if args.round_robin else main_run["costs"], layout=args.partition) if world > 1 else None
         srast = par.ShardedRasterizer(s_static, sharder) if world > 1 else None
         px_mask = srast.pixel_mask().float() if world > 1 else None
         inv_npx = 1.0 / float(H * W)
@@ -887,7 +887,8 @@ def run_ours(args):
         if world == 1:
             fm = MP.FusedMapper(mopt, W, H, cap, deg)
         else:
-            fm = par.DistributedMapper(mopt, W, H, cap, deg, costs=None if args.round_robin else main_run["costs"])
+            fm = par.DistributedMapper(mopt, W, H, cap, deg, costs=None if args.round_robin else main_run["costs"],
+                                      layout=args.partition)
         host_loss = torch.zeros((args.steps + max(3, args.warmup) + 8, 5), dtype=torch.float32).pin_memory()
 
         def map_async(i):
@@ -1016,7 +1017,9 @@ def run_ours(args):
     if world > 1:
         line["exchange"] = ("nvlink peer memory (egs_push_rows: the touched rows stored into the owners' inboxes, device "
                             "barrier, egs_fold_inbox)") if exchange_kind else "nccl reduce_scatter_tensor"
-        line["tile_partition"] = "round-robin tile rows" if args.round_robin else "tile rows balanced by list length"
+        line["tile_partition"] = "round-robin tile rows" if args.round_robin else (
+            "contiguous row-major tile runs of equal summed list length" if args.partition == "bands"
+            else "tile rows balanced by list length")
         line["launch"] = ("the sharded step recorded once per camera cycle into a CUDA graph and replayed (stage_ms: a separate "
                           "eager pass with events)") if graphed_run else "eager launches"
         line["c4"] = c4
@@ -1204,6 +1207,8 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--round-robin", action="store_true", help="N > 1: deal tile rows round-robin instead of by cost")
+    ap.add_argument("--partition", choices=["bands", "rows"], default="bands",
+                    help="N > 1: cost-balanced tile partition layout (parallel.tile_partition)")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the extra C4 (4 M surfels) line")
     ap.add_argument("--no-graph", action="store_true", help="e2e: eager calls only (no torch.cuda.graph replay)")
     ap.add_argument("--no-cpu", action="store_true")

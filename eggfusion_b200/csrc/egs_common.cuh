@@ -4,7 +4,7 @@
 //   geom workspace, per surfel:   SplatRecord rec[P] (64 B, 16-B aligned quads) | cov3D[P][6] f32 |
 //                                 tiles_touched[P] u32 | clamped[P] u8 | cand[P] i32 (sharded projection's candidate list)
 //   img  workspace:               egs_counters (+ticket) | tile_count[T] | tile_offset[T+1] | tile_cursor[T] |
-//                                 tile_list[T] (compacted non-empty tiles) | hit_count[8T] | final_T[N] | final_D[N] |
+//                                 tile_list[T] (compacted non-empty tiles) | hit_count[8T] | mask_bits | final_T[N] | final_D[N] |
 //                                 n_contrib[N]
 //   bin  workspace, per instance: keys[cap] u64 (depth bits << 32 | surfel id, bucketed by tile) | point_list[cap] u32 |
 //                                 hits[8*cap] {surfel id, pixel mask}: per (tile, 8x4 warp block) the compacted, depth-
@@ -98,6 +98,7 @@ struct ImgView {
     uint32_t* tile_cursor;
     int32_t* tile_list;    // [T]
     uint32_t* hit_count;   // [8T] entries of each (tile, warp block) hit list
+    uint32_t* mask_bits;   // [gy][ceil(gx/32)] the frame's tile mask, one bit per tile (rows start at a word; k_pack_mask)
     float* final_T;
     float* final_D;
     uint32_t* n_contrib;
@@ -119,7 +120,7 @@ EGS_HD GeomView carve_geom(void* base, size_t P) {
     v.cov3D = (float*)(b + o);              o = egs_align_up(o + sizeof(float) * 6 * P, 256);
     v.tiles_touched = (uint32_t*)(b + o);   o = egs_align_up(o + sizeof(uint32_t) * P, 256);
     v.clamped = (uint8_t*)(b + o);          o = egs_align_up(o + P, 256);
-    v.cand = (int32_t*)(b + o);             o = egs_align_up(o + sizeof(int32_t) * P, 256);
+    v.cand = (int32_t*)(b + o);             o = egs_align_up(o + sizeof(int32_t) * (P + 2048), 256);   // 32 sub-lists
     v.bytes = o + 256;
     return v;
 }
@@ -134,6 +135,7 @@ EGS_HD ImgView carve_img(void* base, size_t tiles, size_t npix) {
     v.tile_cursor = (uint32_t*)(b + o);     o = egs_align_up(o + 4 * tiles, 256);
     v.tile_list = (int32_t*)(b + o);        o = egs_align_up(o + 4 * tiles, 256);
     v.hit_count = (uint32_t*)(b + o);       o = egs_align_up(o + 32 * tiles, 256);
+    v.mask_bits = (uint32_t*)(b + o);       o = egs_align_up(o + 4 * tiles, 256);   // gy * ceil(gx / 32) <= tiles words
     v.final_T = (float*)(b + o);            o = egs_align_up(o + 4 * npix, 256);
     v.final_D = (float*)(b + o);            o = egs_align_up(o + 4 * npix, 256);
     v.n_contrib = (uint32_t*)(b + o);       o = egs_align_up(o + 4 * npix, 256);
@@ -165,6 +167,22 @@ EGS_HD void egs_tile_rect(float px, float py, int radius, int gx, int gy, int& x
     a = (int)f_mul(f_sub(f_add(f_add(px, r), 16.0f), 1.0f), 0.0625f);        x1 = a < 0 ? 0 : (a > gx ? gx : a);
     a = (int)f_mul(f_sub(f_add(f_add(py, r), 16.0f), 1.0f), 0.0625f);        y1 = a < 0 ? 0 : (a > gy ? gy : a);
 }
+
+// ---- bit-packed tile mask (sharded frames): 1 KB at 1080p, so every lookup is an L1 hit, where the caller's int32 mask
+// (32 KB) kept missing behind the streaming loads of the per-surfel kernels
+EGS_HD int egs_mask_words_per_row(int gx) { return (gx + 31) >> 5; }
+#if defined(__CUDACC__)
+// bits of row y's tiles [x0, x1) that lie in word xw (x0 < x1, xw in [x0 >> 5, (x1 - 1) >> 5])
+__device__ __forceinline__ uint32_t egs_mask_row_word(const uint32_t* __restrict__ bits, int wpr, int y, int xw, int x0,
+                                                      int x1) {
+    const int lo = max(x0 - (xw << 5), 0), hi = min(x1 - (xw << 5), 32);
+    const uint32_t range = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+    return __ldg(bits + y * wpr + xw) & range;
+}
+__device__ __forceinline__ bool egs_mask_bit(const uint32_t* __restrict__ bits, int wpr, int x, int y) {
+    return (__ldg(bits + y * wpr + (x >> 5)) >> (x & 31)) & 1u;
+}
+#endif
 
 // Which reverse-walk kernel runs (EGS_BWD_KERNEL, see egs_render_bwd.cu): 3 = warp (default, consumes per-block hit
 // lists), 0/1/2 = tile-wide variants (consume lane_masks).  The forward writes the format the backward will read.

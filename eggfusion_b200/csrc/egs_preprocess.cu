@@ -35,7 +35,7 @@ __device__ __forceinline__ void unstage_sh_rows(const float* s_sh, float* __rest
 // the reference's radius formula never exceeds 3 sqrt(2 lambda_max + 0.32) (its max(0.1, .) floor) -- so that the ~1500
 // instructions of the exact projection are spent only on the ~1/world of the surfels that can matter to this rank.
 __device__ __forceinline__ bool surfel_misses_mask(const FrameConst& fc, const float* mean, const float* scale,
-                                                   const int32_t* __restrict__ tile_mask) {
+                                                   const uint32_t* __restrict__ mask_bits) {
     const float px = mean[0], py = mean[1], pz = mean[2];
     const float hw = xf_affine(fc.proj, 3, px, py, pz);
     const float vz = xf_affine(fc.view, 2, px, py, pz);
@@ -51,10 +51,26 @@ __device__ __forceinline__ bool surfel_misses_mask(const FrameConst& fc, const f
     if (!(rad < 16384.f)) return false;
     int x0, y0, x1, y1;
     egs_tile_rect(ix, iy, (int)rad, fc.gx, fc.gy, x0, y0, x1, y1);
+    const int w = x1 - x0, h = y1 - y0;
+    if (w <= 0 || h <= 0) return true;                    // the bound rectangle is off the grid
+    if (w * h > 48) return false;                         // a huge splat: not worth walking the mask
+    // no early exit: the loads of one surfel are independent and pipeline (this pass is latency-, not issue-bound)
+    const int wpr = egs_mask_words_per_row(fc.gx);
+    uint32_t any = 0;
     for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++)
-            if (__ldg(tile_mask + y * fc.gx + x) != 0) return false;
-    return true;
+        for (int xw = x0 >> 5; xw <= (x1 - 1) >> 5; xw++) any |= egs_mask_row_word(mask_bits, wpr, y, xw, x0, x1);
+    return any == 0u;
+}
+
+// one bit per tile of the caller's int32 tile mask (rows padded to whole words)
+__global__ void k_pack_mask(const int32_t* __restrict__ tile_mask, int gx, int gy, uint32_t* __restrict__ bits) {
+    const int wpr = egs_mask_words_per_row(gx);
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= wpr * gy) return;
+    const int y = w / wpr, xb = (w % wpr) << 5;
+    uint32_t word = 0;
+    for (int b = 0; b < 32 && xb + b < gx; b++) word |= (__ldg(tile_mask + y * gx + xb + b) != 0 ? 1u : 0u) << b;
+    bits[w] = word;
 }
 
 // Pass 1 of a sharded projection: surfels that cannot reach the rank's tiles (and are not owned) get zero radii /
@@ -62,32 +78,48 @@ __device__ __forceinline__ bool surfel_misses_mask(const FrameConst& fc, const f
 // append, order irrelevant) so that the exact projection runs on dense warps.  Surfel order carries no spatial
 // coherence, so skipping inside the projection kernel itself saves nothing (a warp always contains a surfel that
 // needs the full path: measured, 0.110 -> 0.158 ms at 2 ranks).
+// The list is kept in CAND_REGIONS sub-lists (warp w of the surfel array appends to region w % CAND_REGIONS, which can
+// never hold more than its share of the surfels): one append counter per region instead of one for everything -- the
+// warps of this kernel spent half their time queued behind ~31 k atomics on a single word (ncu), and a CTA-wide
+// aggregation traded that for three barriers per group.
+#define CAND_REGIONS 32
+__host__ __device__ __forceinline__ int cand_region_cap(int P) {
+    const int warps = (P + 31) / 32;
+    return (warps + CAND_REGIONS - 1) / CAND_REGIONS * 32;
+}
+
 __global__ void __launch_bounds__(256)
 k_surfel_candidates(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
-                    const int32_t* __restrict__ tile_mask, int own_first, int own_count, int32_t* __restrict__ radii,
+                    const uint32_t* __restrict__ mask_bits, int own_first, int own_count, int32_t* __restrict__ radii,
                     uint8_t* __restrict__ active, uint32_t* __restrict__ tiles_touched, int32_t* __restrict__ cand,
                     int32_t* __restrict__ cand_count) {
     __shared__ FrameConst fc;
     load_frame_const(fc, f);
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
-    if (i < f.num_surfels) {
-        keep = (i >= own_first && i - own_first < own_count) ||
-               !surfel_misses_mask(fc, means + (size_t)3 * i, scales + (size_t)3 * i, tile_mask);
-        if (!keep) {
-            radii[i] = 0;
-            active[i] = 0;
-            tiles_touched[i] = 0u;
-        }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (bal == 0u) return;
     const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == __ffs(bal) - 1) base = atomicAdd(cand_count, __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-    if (keep) cand[base + __popc(bal & ((1u << lane) - 1u))] = i;
+    const int cap = cand_region_cap(f.num_surfels);
+    // persistent CTAs, grid-stride over 256-surfel groups: the frame constants are fetched once per CTA
+    for (int i0 = blockIdx.x * blockDim.x; i0 < f.num_surfels; i0 += gridDim.x * blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        if (i < f.num_surfels) {
+            keep = (i >= own_first && i - own_first < own_count) ||
+                   !surfel_misses_mask(fc, means + (size_t)3 * i, scales + (size_t)3 * i, mask_bits);
+            if (!keep) {
+                radii[i] = 0;
+                active[i] = 0;
+                tiles_touched[i] = 0u;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal == 0u) continue;
+        const int region = (i >> 5) & (CAND_REGIONS - 1);
+        const int leader = __ffs(bal) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(cand_count + region, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (keep) cand[(size_t)region * cap + base + __popc(bal & ((1u << lane) - 1u))] = i;
+    }
 }
 
 // SH_SMEM = 1: the CTA's SH block (M == 16: 128 x 192 B, contiguous) is staged through shared memory with fully
@@ -109,13 +141,19 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
     __shared__ FrameConst fc;
     __shared__ __align__(128) float s_sh[SH_SMEM >= 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
     __shared__ __align__(8) unsigned long long s_bar;
+    // cand != nullptr (sharded frames): thread j works on surfel cand[j], j < *cand_count -- the surfels a cheap
+    // footprint bound could not rule out (k_surfel_candidates); everything else was zeroed there
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cand) {
+        // CTA (region, q) of the sub-list layout k_surfel_candidates wrote
+        const int cap = cand_region_cap(f.num_surfels);
+        const int per_region = (cap + SURF_THREADS - 1) / SURF_THREADS;
+        const int region = blockIdx.x / per_region, j = (blockIdx.x % per_region) * SURF_THREADS + threadIdx.x;
+        const int n_work = cand_count[region];
+        if (j - (int)threadIdx.x >= n_work) return;             // whole CTA beyond the sub-list (uniform)
+        i = j < n_work ? cand[(size_t)region * cap + j] : f.num_surfels;
+    }
     load_frame_const(fc, f);
-    // cand != nullptr (sharded frames at >= 3 ranks): thread j works on surfel cand[j], j < *cand_count -- the surfels a
-    // cheap footprint bound could not rule out (k_surfel_candidates); everything else was zeroed there
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_work = cand ? *cand_count : f.num_surfels;
-    if (cand && blockIdx.x * blockDim.x >= n_work) return;      // whole CTA beyond the list (uniform)
-    const int i = cand ? (j < n_work ? cand[j] : f.num_surfels) : j;
     const uint32_t bar = smem_addr(&s_bar);
     if (SH_SMEM == 1) {
         const int row0 = blockIdx.x * SURF_THREADS;
@@ -134,6 +172,17 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
             bulk_copy_g2s(smem_addr(s_sh) + 4u * SH_BULK_PITCH * threadIdx.x, shs + (size_t)48 * (row0 + threadIdx.x), 192u, bar);
     }
     const bool valid = i < f.num_surfels;
+    // candidate list: 9 in 10 of its surfels end up needing their SH row, so it is fetched up front and arrives behind the
+    // projection math (deferring it exposed the whole fetch latency: 20 % of the kernel's stall samples)
+    const bool early = SH_SMEM == 3 && cand != nullptr;
+    if (early) {
+        if (valid) {
+            mbar_expect_tx(bar, 192u);
+            bulk_copy_g2s(smem_addr(s_sh) + 4u * SH_BULK_PITCH * threadIdx.x, shs + (size_t)48 * i, 192u, bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    }
     bool visible = false, need = false;
     SurfelFwd o;
     uint32_t cnt = 0;
@@ -146,19 +195,27 @@ k_surfel_forward(const egs_frame f, const float* __restrict__ means, const float
         if (o.radius > 0) {
             visible = true;
             // per-tile instance counts: the histogram that replaces the reference's per-surfel scan
-            for (int y = o.y0; y < o.y1; y++)
-                for (int x = o.x0; x < o.x1; x++) {
-                    const int t = y * fc.gx + x;
-                    if (tile_mask == nullptr || __ldg(tile_mask + t) != 0) {
-                        atomicAdd(im.tile_count + t, 1u);
-                        cnt++;
+            if (tile_mask == nullptr) {
+                for (int y = o.y0; y < o.y1; y++)
+                    for (int x = o.x0; x < o.x1; x++) atomicAdd(im.tile_count + y * fc.gx + x, 1u);
+                cnt = (uint32_t)((o.y1 - o.y0) * (o.x1 - o.x0));
+            } else if (o.x1 > o.x0) {
+                const int wpr = egs_mask_words_per_row(fc.gx);
+                for (int y = o.y0; y < o.y1; y++)
+                    for (int xw = o.x0 >> 5; xw <= (o.x1 - 1) >> 5; xw++) {
+                        uint32_t m = egs_mask_row_word(im.mask_bits, wpr, y, xw, o.x0, o.x1);
+                        cnt += __popc(m);
+                        while (m) {
+                            atomicAdd(im.tile_count + y * fc.gx + (xw << 5) + __ffs(m) - 1, 1u);
+                            m &= m - 1u;
+                        }
                     }
-                }
+            }
             need = cnt > 0u || (i >= own_first && i - own_first < own_count);
         }
         g.tiles_touched[i] = cnt;
     }
-    if (SH_SMEM == 3) {
+    if (SH_SMEM == 3 && !early) {
         // every thread arrives exactly once, before anybody waits: the ones that need their SH row add its bytes
         if (need) {
             mbar_expect_tx(bar, 192u);
@@ -390,21 +447,31 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
         const char* e = getenv("EGS_SH_STAGE");
         sh_bulk = (e && e[0] == 'l') ? 0 : 1;
     }
+    if (tile_mask != nullptr) {
+        // every kernel of the frame looks the mask up through its bit-packed copy (egs_common.cuh)
+        int gx = (f.width + EGS_TILE - 1) / EGS_TILE, gy = (f.height + EGS_TILE - 1) / EGS_TILE;
+        const int words = egs_mask_words_per_row(gx) * gy;
+        k_pack_mask<<<(words + 127) / 128, 128, 0, s>>>(tile_mask, gx, gy, im.mask_bits);
+    }
     const bool sharded = tile_mask != nullptr && own_count < P;   // most SH rows will not be needed: fetch on demand
     if (sh_smem && sharded) {
-        // two passes when the rank owns a third of the surfels or less (>= 3 ranks): candidate compaction
+        // two passes when the rank owns a third of the surfels or less (>= 3 ranks; measured at 2 ranks: the candidate
+        // pass costs more than the projection of the ~25 % of the surfels it rules out): candidate compaction
         // (k_surfel_candidates), then the exact projection on the candidates only, on dense warps
         static int two_pass = -1;
         if (two_pass < 0) {
-            const char* e = getenv("EGS_SHARD_TWO_PASS");   // "0": never, "1": always (tests), default: own_count <= P / 3
+            const char* e = getenv("EGS_SHARD_TWO_PASS");   // "0": never, "1": always, default: own_count <= P / 3
             two_pass = e ? (e[0] == '1' ? 1 : 0) : 2;
         }
-        if (two_pass == 1 || (two_pass == 2 && (long long)own_count * 3 <= (long long)P)) {
-            int32_t* cand_count = reinterpret_cast<int32_t*>(im.ticket);   // zeroed by the plan's head memset
-            k_surfel_candidates<<<(P + 255) / 256, 256, 0, s>>>(f, means, scales, tile_mask, own_first, own_count, radii,
-                                                                active, g.tiles_touched, g.cand, cand_count);
-            k_surfel_forward<3><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
-                                                                im, radii, active, own_first, own_count, g.cand, cand_count);
+        if (two_pass == 1 || (two_pass == 2 && (long long)own_count * 3 <= (long long)P + 768)) {
+            int32_t* cand_count = reinterpret_cast<int32_t*>(im.ticket);   // CAND_REGIONS words, zeroed by the plan's head memset
+            const int groups = (P + 255) / 256;
+            k_surfel_candidates<<<groups < 148 * 8 ? groups : 148 * 8, 256, 0, s>>>(
+                f, means, scales, im.mask_bits, own_first, own_count, radii, active, g.tiles_touched, g.cand, cand_count);
+            const int per_region = (cand_region_cap(P) + SURF_THREADS - 1) / SURF_THREADS;
+            k_surfel_forward<3><<<CAND_REGIONS * per_region, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors,
+                                                                          tile_mask, g, im, radii, active, own_first,
+                                                                          own_count, g.cand, cand_count);
         } else
             k_surfel_forward<3><<<(P + 127) / 128, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors, tile_mask, g,
                                                                 im, radii, active, own_first, own_count, nullptr, nullptr);

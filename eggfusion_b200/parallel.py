@@ -35,15 +35,30 @@ from ._lib import SCREEN_GRAD_STRIDE
 
 # ------------------------------------------------------------------------------------------------- partitions
 def tile_partition(tiles_y: int, tiles_x: int, world: int, rank: int,
-                   costs: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   costs: Optional[torch.Tensor] = None, layout: str = "bands") -> torch.Tensor:
     """int32 [tiles_y, tiles_x] mask of the tiles rank `rank` renders.  Masks of all ranks are disjoint and cover
-    the grid.  Without `costs`: tile rows are dealt round-robin.  With `costs` (per-tile list lengths, any
-    device): rows are assigned greedily (longest-processing-time first) to balance the summed cost."""
+    the grid.  Without `costs`: tile rows are dealt round-robin.  With `costs` (per-tile list lengths, any device):
+      layout "bands" (default): the row-major tile sequence is cut into `world` CONTIGUOUS runs of equal summed cost
+        (balance to one tile).  A surfel's tile rectangle then meets one rank, two at a band edge -- so the sharded
+        projection keeps ~1/world of the surfels per rank (egs_forward_plan_sharded) and a surfel's screen-gradient
+        row is pushed to its owner once, not once per tile row it spans;
+      layout "rows": whole tile rows assigned greedily, longest first (rows of one rank are scattered over the image)."""
     mask = torch.zeros((tiles_y, tiles_x), dtype=torch.int32)
     if costs is None:
         mask[rank::world, :] = 1
         return mask
-    row_cost = costs.detach().to("cpu", torch.float64).reshape(tiles_y, tiles_x).sum(dim=1)
+    c = costs.detach().to("cpu", torch.float64).reshape(tiles_y, tiles_x)
+    if layout == "bands":
+        # a tile costs its list length plus a constant (an empty tile still occupies a CTA slot for a moment)
+        flat = c.reshape(-1) + 1.0
+        cum = torch.cumsum(flat, 0)
+        total = float(cum[-1])
+        mid = cum - 0.5 * flat                                  # a tile belongs to the run its midpoint falls in
+        owner = torch.clamp((mid * (world / total)).floor().long(), 0, world - 1)
+        return (owner == rank).to(torch.int32).reshape(tiles_y, tiles_x)
+    if layout != "rows":
+        raise ValueError("tile_partition: layout must be 'bands' or 'rows'")
+    row_cost = c.sum(dim=1)
     order = torch.argsort(row_cost, descending=True, stable=True).tolist()
     load = [0.0] * world
     owner = [0] * tiles_y
@@ -222,17 +237,18 @@ class ShardedSplat:
     """One rank's share of a tile-sharded forward + backward (fresh tensors per call, like rasterizer.forward_raw).
     CUDA only."""
 
-    def __init__(self, group=None, costs: Optional[torch.Tensor] = None):
+    def __init__(self, group=None, costs: Optional[torch.Tensor] = None, layout: str = "bands"):
         self.group = group
         self.world, self.rank = _world_rank(group)
         self.costs = costs
+        self.layout = layout
         self._mask_cache = {}
         self._exchange = {}
 
     def mask_for(self, tiles_y: int, tiles_x: int, device) -> torch.Tensor:
         key = (tiles_y, tiles_x, str(device))
         if key not in self._mask_cache:
-            self._mask_cache[key] = tile_partition(tiles_y, tiles_x, self.world, self.rank, self.costs).to(device)
+            self._mask_cache[key] = tile_partition(tiles_y, tiles_x, self.world, self.rank, self.costs, self.layout).to(device)
         return self._mask_cache[key]
 
     def set_costs(self, costs: Optional[torch.Tensor]) -> None:
@@ -371,7 +387,7 @@ class DistributedMapper:
     refreshed everywhere by the all-gather)."""
 
     def __init__(self, opt, width: int, height: int, capacity: int, sh_degree: int, group=None,
-                 costs: Optional[torch.Tensor] = None):
+                 costs: Optional[torch.Tensor] = None, layout: str = "bands"):
         from . import _lib
         from .pipeline import SplatContext
         self.opt, self.group = opt, group
@@ -381,7 +397,7 @@ class DistributedMapper:
         self.first, self.count = surfel_range(P, self.world, self.rank)
         self.chunk = padded_rows(P, self.world) // self.world
         ty, tx = (height + 15) // 16, (width + 15) // 16
-        self.tile_mask = tile_partition(ty, tx, self.world, self.rank, costs).to(dev) if self.world > 1 else None
+        self.tile_mask = tile_partition(ty, tx, self.world, self.rank, costs, layout).to(dev) if self.world > 1 else None
         self.exchange = make_exchange(P, dev, group) if self.world > 1 else None
         self.ctx = SplatContext(P, width, height, opt.M, capacity, device=dev, padded_rows=padded_rows(P, self.world),
                                 own_range=(self.first, self.count) if self.world > 1 else None)

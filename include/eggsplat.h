@@ -150,6 +150,8 @@ EGS_API int egs_fold_inbox(int32_t chunk_rows, int32_t world, int32_t first, con
  * instances (see egs_workspace_sizes); if the true count is larger the lists are truncated and
  * counters.overflow is set.  All four images are fully written (tiles without surfels get zeros, like the
  * reference's zero-initialised outputs), so the caller may pass uninitialised memory.
+ * `tile_mask` must be the mask the frame's egs_forward_plan was given (NULL with NULL): the plan leaves a bit-packed
+ * copy of it in `img` which the emission reads.
  */
 EGS_API int egs_forward_render(const egs_frame* frame, const int32_t* tile_mask, const int32_t* radii, void* geom, void* img,
                        void* bin, int64_t cap_instances, float* out_color, float* out_normal, float* out_depth,

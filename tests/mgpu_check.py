@@ -64,7 +64,9 @@ def main():
     mode = "peer" if par.make_exchange(16, dev) is not None else "nccl"
 
     # ---- 1. raw level, two steps (the second one exercises the alternate exchange block and the self-cleaning)
-    sh = par.ShardedSplat()
+    # uniform costs -> contiguous row-major tile runs of equal length (the default "bands" layout, cut mid-row)
+    uniform = torch.ones(((H + 15) // 16) * ((W + 15) // 16), dtype=torch.float64)
+    sh = par.ShardedSplat(costs=uniform)
     for step in range(2):
         color, normal, depth, opacity, st = sh.forward(s, means, shs, empty, opac, scales, rots)
         grads, (first, count) = sh.backward(st, means, shs, empty, scales, rots, *gt)
@@ -127,7 +129,7 @@ def main():
     del out
     mopt = MP.FrameBatchOptimizer(raw, MP.LrParams(**bench.MAP_LR), MP.MappingWeights(**bench.MAP_WEIGHTS),
                                   padded_rows=par.padded_rows(P, world))
-    dm = par.DistributedMapper(mopt, W, H, cap, deg_b)
+    dm = par.DistributedMapper(mopt, W, H, cap, deg_b, costs=uniform)
     losses = []
     for i in range(iters):
         losses.append(dm.iterate(settings[i % len(settings)], *frames[i % len(frames)]).clone())

@@ -21,16 +21,35 @@ def test_tile_partition_is_a_partition():
         assert all(m.dtype == torch.int32 for m in masks)
 
 
-def test_cost_balanced_partition():
+@pytest.mark.parametrize("layout", ["bands", "rows"])
+def test_cost_balanced_partition(layout):
     ty, tx, world = 40, 30, 4
     rng = np.random.default_rng(0)
     costs = torch.from_numpy(rng.pareto(1.5, size=(ty, tx)) * 100)
-    masks = [par.tile_partition(ty, tx, world, r, costs) for r in range(world)]
+    masks = [par.tile_partition(ty, tx, world, r, costs, layout) for r in range(world)]
     assert torch.equal(torch.stack(masks).sum(0), torch.ones((ty, tx), dtype=torch.int32))
     loads = torch.tensor([float((costs * m).sum()) for m in masks])
     naive = torch.tensor([float((costs * par.tile_partition(ty, tx, world, r)).sum()) for r in range(world)])
     assert loads.max() <= naive.max() + 1e-9
-    assert loads.max() / loads.mean() < 1.25
+    assert loads.max() / loads.mean() < (1.05 if layout == "bands" else 1.25)
+    if layout == "bands":
+        # every rank's tiles are ONE contiguous run of the row-major sequence, in rank order
+        owner = torch.stack(masks).argmax(0).reshape(-1)
+        assert bool((owner[1:] >= owner[:-1]).all())
+    with pytest.raises(ValueError):
+        par.tile_partition(ty, tx, world, 0, costs, "diagonal")
+
+
+def test_band_partition_degenerate_costs():
+    """All-zero costs (nothing rendered yet) still give every rank a run; one tile holding all the cost goes to one rank."""
+    ty, tx, world = 9, 7, 8
+    masks = [par.tile_partition(ty, tx, world, r, torch.zeros(ty * tx)) for r in range(world)]
+    assert torch.equal(torch.stack(masks).sum(0), torch.ones((ty, tx), dtype=torch.int32))
+    assert all(int(m.sum()) >= ty * tx // world - 1 for m in masks)
+    spike = torch.zeros(ty * tx)
+    spike[20] = 1e9
+    masks = [par.tile_partition(ty, tx, world, r, spike) for r in range(world)]
+    assert torch.equal(torch.stack(masks).sum(0), torch.ones((ty, tx), dtype=torch.int32))
 
 
 def test_surfel_ranges_cover_exactly():
