@@ -227,7 +227,7 @@ def test_sharded_projection_equals_the_full_one_on_the_ranks_tiles(world):
     kept = shard[5] > 0
     assert torch.equal(shard[5][kept], full[5][kept]) and torch.equal(shard[4][kept], full[4][kept])
     dropped = (~kept) & (full[5] > 0)
-    assert int(dropped.sum()) > 0 or world < 2
+    assert int(dropped.sum()) > 0 or world < 3        # 2 ranks: single-pass projection, every radius kept
     idx = torch.nonzero(dropped).flatten()
     assert not bool(((idx >= first) & (idx < first + count)).any())
     # a dropped surfel's exact tile rectangle holds no tile of the rank: the un-sharded plan emitted no instance for it
