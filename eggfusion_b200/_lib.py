@@ -103,6 +103,7 @@ SIGNATURES.update({
     "egm_loss_seed": (C.c_int, [_I32, _I32] + [_P] * 8 + [C.c_float] * 3 + [_P] * 5),
     "egm_loss_seed_tiles": (C.c_int, [_I32, _I32] + [_P] * 9 + [C.c_float] * 3 + [_P] * 5),
     "egm_adam_step": (C.c_int, [_I32, _I32, C.POINTER(AdamHyper)] + [_P] * 27),
+    "egm_backward_surfels_adam": (C.c_int, [C.POINTER(Frame), _I32, _I32] + [_P] * 11 + [C.POINTER(AdamHyper), _P, _P, _P]),
     "egm_activate": (C.c_int, [_I32] + [_P] * 8),
     "egm_loss_total": (C.c_int, [_P, _P, _I32, _I32] + [C.c_float] * 5 + [_I32, _I32, _P, _P]),
 })

@@ -209,8 +209,10 @@ struct EgmAdamConst {
 };
 // neg_step_size = -(lr / (1 - beta1^t)), bc2_sqrt = sqrt(1 - beta2^t) (computed in double on the host, like torch)
 EGS_HD float egm_adam_update(float p, float g, float& m, float& v, const EgmAdamConst& c, float neg_step_size) {
-    m = m + c.one_m_beta1 * (g - m);              // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5 branch
-    v = v * c.beta2 + c.one_m_beta2 * g * g;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float denom = egm_div(egm_sqrt(v), c.bc2_sqrt) + c.eps;
-    return p + neg_step_size * egm_div(m, denom);       // param.addcdiv_(exp_avg, denom, value=-step_size)
+    // explicit roundings (the contraction nvcc applies to torch's kernels), so that every kernel this is inlined into --
+    // k_adam_sh, k_adam_geom, the fused k_surfel_backward -- produces the same bits
+    m = f_fma(c.one_m_beta1, f_sub(g, m), m);                       // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5 branch
+    v = f_fma(f_mul(c.one_m_beta2, g), g, f_mul(v, c.beta2));       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    const float denom = f_add(egm_div(egm_sqrt(v), c.bc2_sqrt), c.eps);
+    return f_fma(neg_step_size, egm_div(m, denom), p);              // param.addcdiv_(exp_avg, denom, value=-step_size)
 }

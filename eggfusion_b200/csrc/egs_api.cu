@@ -1,6 +1,7 @@
 // egs_api.cu -- the extern "C" surface declared in include/eggsplat.h.  Argument checking, workspace carving and
 // kernel sequencing only; no allocation, no device synchronisation, no exceptions.
 #include "egs_common.cuh"
+#include "../../include/eggmap.h"
 
 cudaError_t launch_surfel_forward(const egs_frame&, const float*, const float*, const float*, const float*, const float*,
                                   const float*, const int32_t*, GeomView, ImgView, int32_t*, uint8_t*, int, int,
@@ -8,6 +9,9 @@ cudaError_t launch_surfel_forward(const egs_frame&, const float*, const float*, 
 cudaError_t launch_surfel_backward(const egs_frame&, int, int, const float*, const float*, const float*, const float*,
                                    const float*, const int32_t*, GeomView, const float*, float*, float*, float*, float*,
                                    float*, float*, float*, float*, cudaStream_t);
+cudaError_t launch_surfel_backward_adam(const egs_frame&, int, int, const float*, float*, const float*, const float*,
+                                        const int32_t*, GeomView, const float*, float*, float*, float*, float*, float*,
+                                        float*, double, double, double, int, float, float, cudaStream_t);
 cudaError_t launch_mark_visible(int, const float*, const float*, const float*, uint8_t*, cudaStream_t);
 cudaError_t launch_tile_scan(ImgView, int, long long, cudaStream_t);
 cudaError_t launch_emit_sort(int, int, int, const int32_t*, GeomView, const int32_t*, ImgView, BinView, long long,
@@ -276,6 +280,30 @@ EGS_API int egs_backward_surfels(const egs_frame* f, int32_t first, int32_t coun
     EGS_TRY(launch_surfel_backward(*f, first, count, means3D, shs, colors_precomp, scales, rotations, radii, g,
                                    screen_grads, dL_dmeans3D, dL_dopacity, dL_dsh, dL_dscales, dL_drotations,
                                    dL_dmeans2D, dL_dcolors, dL_dcov3D, (cudaStream_t)stream));
+    return 0;
+}
+
+EGS_API int egm_backward_surfels_adam(const egs_frame* f, int32_t first, int32_t count, const float* means3D, float* shs,
+                                      const float* scales, const float* rotations, const int32_t* radii,
+                                      const void* geom, const float* screen_grads, float* dL_dmeans3D,
+                                      float* dL_dopacity, float* dL_dscales, float* dL_drotations,
+                                      const egm_adam* hyper, float* m_shs, float* v_shs, void* stream) {
+    int rc = check_frame(f);
+    if (rc) return rc;
+    const int P = f->num_surfels;
+    if (first < 0 || count < 0 || first + count > P || !hyper || hyper->step < 1) return EGS_E_BADARG;
+    if (count == 0) return 0;
+    if (!means3D || !shs || !scales || !rotations || !radii || !geom || !screen_grads || !m_shs || !v_shs) return EGS_E_BADARG;
+    if (!dL_dmeans3D || !dL_dopacity || !dL_dscales || !dL_drotations) return EGS_E_BADARG;
+    // the fused form exists for the layout the mapping loop uses: 16 SH coefficients, 16-byte aligned rows
+    if (f->sh_coeffs != 16 || ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(m_shs) |
+                                reinterpret_cast<uintptr_t>(v_shs)) & 15) != 0)
+        return EGS_E_UNSUPPORTED;
+    GeomView g = carve_geom(const_cast<void*>(geom), (size_t)P);
+    EGS_TRY(launch_surfel_backward_adam(*f, first, count, means3D, shs, scales, rotations, radii, g, screen_grads,
+                                        dL_dmeans3D, dL_dopacity, dL_dscales, dL_drotations, m_shs, v_shs, hyper->beta1,
+                                        hyper->beta2, hyper->eps, hyper->step, hyper->lr_f_dc, hyper->lr_f_rest,
+                                        (cudaStream_t)stream));
     return 0;
 }
 

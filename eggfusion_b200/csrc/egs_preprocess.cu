@@ -5,6 +5,7 @@
 // Replaces preprocessCUDA<3> (DGS/cuda_rasterizer/forward.cu:158-301), computeCov2DCUDA + preprocessCUDA<3> (bwd)
 // (DGS/cuda_rasterizer/backward.cu:144-416) and checkFrustum (DGS/cuda_rasterizer/rasterizer_impl.cu:54-66).
 #include "egs_surfel_math.cuh"
+#include "egm_math.cuh"
 #include <stdlib.h>
 
 #define SURF_THREADS 128
@@ -24,6 +25,36 @@ __device__ __forceinline__ void unstage_sh_rows(const float* s_sh, float* __rest
     for (int idx = threadIdx.x; idx < rows * 12; idx += SURF_THREADS) {
         const float* d = s_sh + (idx / 12) * SH_PITCH + 4 * (idx % 12);
         dst4[idx] = make_float4(d[0], d[1], d[2], d[3]);
+    }
+}
+
+// Fused optimiser step of the mapping iteration (egm_backward_surfels_adam, include/eggmap.h): the CTA's dL/dSH block is
+// consumed where it was produced -- Adam on the SH rows straight out of shared memory -- instead of being written to
+// HBM and read back by a separate pass (192 B/surfel each way, plus one launch).  m == nullptr: plain backward.
+struct ShAdam {
+    float* p;      // SH parameters [P][16][3] (the array the kernel's `shs` input points at), updated in place
+    float* m;      // exp_avg
+    float* v;      // exp_avg_sq
+    EgmAdamConst c;
+    float nss_dc, nss_rest;   // -(lr / (1 - beta1^t)) of row 0 (f_dc) and of rows 1..15 (f_rest)
+};
+// The parameter quad is re-read from global memory (the staged copy was overwritten in place by the gradient): the
+// CTA fetched it a few microseconds ago, so it is an L2 hit.
+__device__ __forceinline__ void adam_sh_rows(const float* s_sh, const ShAdam& a, size_t row0, int rows) {
+    float4* p4 = reinterpret_cast<float4*>(a.p + 48 * row0);
+    float4* m4 = reinterpret_cast<float4*>(a.m + 48 * row0);
+    float4* v4 = reinterpret_cast<float4*>(a.v + 48 * row0);
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < rows * 12; idx += SURF_THREADS) {
+        const int q = idx % 12;
+        const float* d = s_sh + (idx / 12) * SH_PITCH + 4 * q;
+        float4 p = p4[idx], m = m4[idx], v = v4[idx];
+        // columns 0..2 of a row are f_dc (SH coefficient 0, three channels), the rest f_rest
+        p.x = egm_adam_update(p.x, d[0], m.x, v.x, a.c, q == 0 ? a.nss_dc : a.nss_rest);
+        p.y = egm_adam_update(p.y, d[1], m.y, v.y, a.c, q == 0 ? a.nss_dc : a.nss_rest);
+        p.z = egm_adam_update(p.z, d[2], m.z, v.z, a.c, q == 0 ? a.nss_dc : a.nss_rest);
+        p.w = egm_adam_update(p.w, d[3], m.w, v.w, a.c, a.nss_rest);
+        p4[idx] = p; m4[idx] = m; v4[idx] = v;
     }
 }
 
@@ -275,7 +306,8 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
                   const float* __restrict__ rots, const int32_t* __restrict__ radii, GeomView g,
                   const float* __restrict__ sg, float* __restrict__ d_means, float* __restrict__ d_opacity,
                   float* __restrict__ d_sh, float* __restrict__ d_scales, float* __restrict__ d_rots,
-                  float* __restrict__ d_means2D, float* __restrict__ d_colors, float* __restrict__ d_cov3D) {
+                  float* __restrict__ d_means2D, float* __restrict__ d_colors, float* __restrict__ d_cov3D,
+                  const ShAdam adam) {
     __shared__ FrameConst fc;
     __shared__ __align__(128) float s_sh[SH_SMEM == 2 ? SURF_THREADS * SH_BULK_PITCH : (SH_SMEM ? SURF_THREADS * SH_PITCH : 1)];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -400,7 +432,8 @@ k_surfel_backward(const egs_frame f, int first, int count, const float* __restri
     }
     if (SH_SMEM == 1) {
         __syncthreads();
-        unstage_sh_rows(s_sh, d_sh + (size_t)48 * row0, rows); // coalesced 16-byte stores of the CTA's dL/dSH block
+        if (adam.m != nullptr) adam_sh_rows(s_sh, adam, (size_t)row0, rows);
+        else unstage_sh_rows(s_sh, d_sh + (size_t)48 * row0, rows); // coalesced 16-byte stores of the CTA's dL/dSH block
     }
     if (SH_SMEM == 2) {
         mbar_wait(bar, 0u);   // no copy into this CTA's shared memory may be in flight when it retires
@@ -500,18 +533,43 @@ cudaError_t launch_surfel_backward(const egs_frame& f, int first, int count, con
         const char* e = getenv("EGS_SH_STAGE");
         sh_bulk = (e && e[0] == 'b') ? 1 : 0;
     }
+    ShAdam none;
+    none.p = none.m = none.v = nullptr;
     if (sh_smem && sh_bulk)
         k_surfel_backward<2><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
                                                                  radii, g, sg, d_means, d_opacity, d_sh, d_scales,
-                                                                 d_rots, d_means2D, d_colors, d_cov3D);
+                                                                 d_rots, d_means2D, d_colors, d_cov3D, none);
     else if (sh_smem)
         k_surfel_backward<1><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
                                                                     radii, g, sg, d_means, d_opacity, d_sh, d_scales,
-                                                                    d_rots, d_means2D, d_colors, d_cov3D);
+                                                                    d_rots, d_means2D, d_colors, d_cov3D, none);
     else
         k_surfel_backward<0><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, colors, scales, rots,
                                                                      radii, g, sg, d_means, d_opacity, d_sh, d_scales,
-                                                                     d_rots, d_means2D, d_colors, d_cov3D);
+                                                                     d_rots, d_means2D, d_colors, d_cov3D, none);
+    return cudaGetLastError();
+}
+
+// per-surfel backward + Adam on the SH block in one kernel; shs is read AND updated (16 coefficients, 16-byte aligned)
+cudaError_t launch_surfel_backward_adam(const egs_frame& f, int first, int count, const float* means, float* shs,
+                                        const float* scales, const float* rots, const int32_t* radii, GeomView g,
+                                        const float* sg, float* d_means, float* d_opacity, float* d_scales,
+                                        float* d_rots, float* m_sh, float* v_sh, double beta1, double beta2, double eps,
+                                        int step, float lr_dc, float lr_rest, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    ShAdam a;
+    a.p = shs; a.m = m_sh; a.v = v_sh;
+    // torch computes the bias corrections and the step size in double on the host (optim/adam.py); same as egm_adam_step
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    a.c.beta1 = (float)beta1; a.c.beta2 = (float)beta2;
+    a.c.one_m_beta1 = (float)(1.0 - beta1); a.c.one_m_beta2 = (float)(1.0 - beta2);
+    a.c.eps = (float)eps; a.c.bc2_sqrt = (float)sqrt(bc2);
+    a.nss_dc = (float)(-((double)lr_dc / bc1));
+    a.nss_rest = (float)(-((double)lr_rest / bc1));
+    k_surfel_backward<1><<<(count + 127) / 128, 128, 0, s>>>(f, first, count, means, shs, nullptr, scales, rots, radii, g,
+                                                             sg, d_means, d_opacity, nullptr, d_scales, d_rots, nullptr,
+                                                             nullptr, nullptr, a);
     return cudaGetLastError();
 }
 

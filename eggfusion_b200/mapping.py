@@ -213,7 +213,7 @@ class FrameBatchOptimizer:
                               lr.feature_lr / 20.0, lr.opacity_lr, lr.scaling_lr, lr.rotation_lr, self.step_count,
                               w.reg_weight, w.reg_weight_n)
 
-    def step(self, grads=None, first: int = 0, count: Optional[int] = None) -> None:
+    def step(self, grads=None, first: int = 0, count: Optional[int] = None, _sh_done: bool = False) -> None:
         """optimizer.step() + optimizer.zero_grad(): `grads` = dict xyz, shs, opacity, scales, rotations of gradients
         w.r.t. the activated parameters (default: the .grad of `total_params`).
         `first`, `count`: update only the surfel rows [first, first + count) (a rank's owned range in a sharded
@@ -224,7 +224,8 @@ class FrameBatchOptimizer:
             zero = lambda t: torch.zeros_like(t)
             grads = {k: (tp[k].grad if tp[k].grad is not None else zero(tp[k])) for k in tp}
         g = {k: _cuda_f32(v, "grad " + k) for k, v in grads.items()}
-        self.step_count += 1
+        if not _sh_done:
+            self.step_count += 1
         h = self._hyper()
         st = self.state
         dev = self.device
@@ -234,12 +235,15 @@ class FrameBatchOptimizer:
             h.reg_weight_n = h.reg_weight_n * (count / self.P)
         M3 = self.M * 3
         at = lambda t, width: t.data_ptr() + 4 * width * first      # row `first` of a [P, width] fp32 array
+        sh = not _sh_done
         with torch.cuda.device(dev), torch.no_grad():
             _lib.check(self.lib.egm_adam_step(
-                count, self.M, C.byref(h), at(self.xyz, 3), at(self.shs, M3), at(self.opacity_raw, 1),
-                at(self.scaling_raw, 3), at(self.rotation_raw, 4), at(g["xyz"], 3), at(g["shs"], M3),
+                count, self.M if sh else 0, C.byref(h), at(self.xyz, 3), at(self.shs, M3) if sh else None,
+                at(self.opacity_raw, 1),
+                at(self.scaling_raw, 3), at(self.rotation_raw, 4), at(g["xyz"], 3), at(g["shs"], M3) if sh else None,
                 at(g["opacity"], 1), at(g["scales"], 3), at(g["rotations"], 4),
-                at(st["xyz"][0], 3), at(st["xyz"][1], 3), at(st["shs"][0], M3), at(st["shs"][1], M3),
+                at(st["xyz"][0], 3), at(st["xyz"][1], 3), at(st["shs"][0], M3) if sh else None,
+                at(st["shs"][1], M3) if sh else None,
                 at(st["opacity"][0], 1), at(st["opacity"][1], 1), at(st["scaling"][0], 3),
                 at(st["scaling"][1], 3), at(st["rotation"][0], 4), at(st["rotation"][1], 4),
                 at(self.pos0, 3), at(self.normal0, 3), self.reg.data_ptr(), at(self.opacity, 1),
@@ -247,6 +251,34 @@ class FrameBatchOptimizer:
         if self._leaves is not None:
             for t in self._leaves.values():
                 t.grad = None
+
+    @property
+    def can_fuse_sh(self) -> bool:
+        """egm_backward_surfels_adam covers the layout the mapping loop uses: 16 SH coefficients, 16-byte aligned."""
+        st = self.state["shs"]
+        return self.M == 16 and all(t.data_ptr() % 16 == 0 for t in (self.shs, st[0], st[1]))
+
+    def backward_surfels_and_step(self, ctx, first: int = 0, count: Optional[int] = None,
+                                  screen_base: Optional[int] = None, mark=None) -> None:
+        """The per-surfel backward of `ctx`'s frame and optimizer.step() as two launches: k_surfel_backward applies
+        Adam to the SH block while the gradient rows are still in shared memory (egm_backward_surfels_adam), the other
+        four groups follow in k_adam_geom.  Same results as ctx.backward_surfels() + step() (bit-identical: the same
+        update function on the same gradient)."""
+        count = self.P - first if count is None else int(count)
+        self.step_count += 1
+        h = self._hyper()
+        st = self.state["shs"]
+        with torch.cuda.device(self.device), torch.no_grad():
+            _lib.check(self.lib.egm_backward_surfels_adam(
+                C.byref(ctx.frame), first, count, self.xyz.data_ptr(), self.shs.data_ptr(), self.scales.data_ptr(),
+                self.rotations.data_ptr(), ctx.radii.data_ptr(), ctx.geom.data_ptr(),
+                ctx.screen.data_ptr() if screen_base is None else screen_base, ctx.d_means.data_ptr(),
+                ctx.d_opac.data_ptr(), ctx.d_scales.data_ptr(), ctx.d_rots.data_ptr(), C.byref(h), st[0].data_ptr(),
+                st[1].data_ptr(), R._stream_ptr(self.device)), "backward_surfels_adam")
+        if mark:
+            mark("bwd_surfels")
+        self.step({"xyz": ctx.d_means, "opacity": ctx.d_opac, "scales": ctx.d_scales, "rotations": ctx.d_rots},
+                  first=first, count=count, _sh_done=True)
 
     def loss_values(self, terms, have_depth=True, have_normal=True):
         """float32[5] device tensor: total, color, depth, normal, reg of the iteration just stepped (no host sync)."""
@@ -273,8 +305,12 @@ class FusedMapper:
     every frame's counters follow the render to pinned host memory and the NEXT iterate() (or synchronize()) raises if
     one of them carried the overflow flag."""
 
-    def __init__(self, opt: FrameBatchOptimizer, width: int, height: int, capacity: int, sh_degree: int):
+    def __init__(self, opt: FrameBatchOptimizer, width: int, height: int, capacity: int, sh_degree: int,
+                 fuse_sh_adam: Optional[bool] = None):
+        """fuse_sh_adam: apply Adam to the SH block inside the per-surfel backward kernel (default: whenever the layout
+        allows it, FrameBatchOptimizer.can_fuse_sh); False keeps the two separate passes."""
         self.opt = opt
+        self.fuse_sh_adam = opt.can_fuse_sh if fuse_sh_adam is None else bool(fuse_sh_adam)
         self.ctx = SplatContext(opt.P, width, height, opt.M, capacity, device=opt.device)
         self.sh_degree = sh_degree
         dev = opt.device
@@ -295,9 +331,12 @@ class FusedMapper:
             if mark:
                 mark("loss_seed")
             ctx.backward_render(self.g_color, self.g_normal, self.g_depth, self.g_opac, mark=mark)
-            ctx.backward_surfels(o.xyz, o.shs, None, o.scales, o.rotations, mark=mark)
-            o.step({"xyz": ctx.d_means, "shs": ctx.d_sh, "opacity": ctx.d_opac, "scales": ctx.d_scales,
-                    "rotations": ctx.d_rots})
+            if self.fuse_sh_adam:
+                o.backward_surfels_and_step(ctx, mark=mark)
+            else:
+                ctx.backward_surfels(o.xyz, o.shs, None, o.scales, o.rotations, mark=mark)
+                o.step({"xyz": ctx.d_means, "shs": ctx.d_sh, "opacity": ctx.d_opac, "scales": ctx.d_scales,
+                        "rotations": ctx.d_rots})
             if mark:
                 mark("adam")
             return o.loss_values(self.terms, frame_input.get("depth_map") is not None,

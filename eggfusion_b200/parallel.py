@@ -423,9 +423,13 @@ class DistributedMapper:
             MP.loss_seed(ctx.color, ctx.depth, ctx.normal, frame_input["color_map"], frame_input.get("depth_map"),
                          frame_input.get("normal_map_c"), render_mask[0], render_mask[1], o.weights,
                          out=(self.terms, self.g_color, self.g_depth, self.g_normal), tile_mask=self.tile_mask)
+            fused = o.can_fuse_sh
             if self.world == 1:
                 ctx.backward_render(self.g_color, self.g_normal, self.g_depth, self.g_opac)
-                ctx.backward_surfels(o.xyz, o.shs, None, o.scales, o.rotations)
+                if fused:
+                    o.backward_surfels_and_step(ctx)
+                else:
+                    ctx.backward_surfels(o.xyz, o.shs, None, o.scales, o.rotations)
             else:
                 ctx.backward_render(self.g_color, self.g_normal, self.g_depth, self.g_opac, prezeroed=self.exchange is not None)
                 stream = R._stream_ptr(o.device)
@@ -434,11 +438,16 @@ class DistributedMapper:
                 else:
                     mine = reduce_scatter_rows(ctx.screen, self.group)
                     base = mine.data_ptr() - self.rank * self.chunk * SCREEN_GRAD_STRIDE * 4
-                ctx.backward_surfels(o.xyz, o.shs, None, o.scales, o.rotations, self.first, self.count, screen_base=base)
+                if fused:
+                    o.backward_surfels_and_step(ctx, self.first, self.count, screen_base=base)
+                else:
+                    ctx.backward_surfels(o.xyz, o.shs, None, o.scales, o.rotations, self.first, self.count,
+                                         screen_base=base)
                 if self.exchange is not None:
                     self.exchange.consumed()
-            o.step({"xyz": ctx.d_means, "shs": ctx.d_sh, "opacity": ctx.d_opac, "scales": ctx.d_scales,
-                    "rotations": ctx.d_rots}, first=self.first, count=self.count)
+            if not fused:
+                o.step({"xyz": ctx.d_means, "shs": ctx.d_sh, "opacity": ctx.d_opac, "scales": ctx.d_scales,
+                        "rotations": ctx.d_rots}, first=self.first, count=self.count)
             if self.world > 1:
                 # the regulariser's norms and the image terms are sums over surfels / pixels: add the ranks' parts
                 # (only the two slots this step wrote: the other norm slot already holds a global sum)

@@ -90,6 +90,20 @@ EGS_API int egm_adam_step(int32_t P, int32_t sh_coeffs, const egm_adam* hyper, f
                           const float* normal0, double* reg, float* opacity, float* scales, float* rotations,
                           void* stream);
 
+/* Per-surfel backward of the rasterizer (egs_backward_surfels, include/eggsplat.h) for surfels [first, first + count)
+ * with the Adam update of the SH block (the f_dc / f_rest groups of GaussianSurfels.parametrize,
+ * gaussian_surfels.py:134-150; torch.optim.Adam as in egm_adam_step) applied in the same kernel: dL/dSH is consumed
+ * from shared memory and never reaches HBM (saves 384 B/surfel of traffic and one launch per mapping iteration).
+ * `shs` [P][16][3] is read by the backward and updated in place, m_shs / v_shs are its Adam state (pointers to row 0:
+ * the call offsets them by `first` itself); the other gradients are written like egs_backward_surfels does.
+ * Follow it with egm_adam_step(..., sh_coeffs = 0, ...) for the remaining four groups, SAME hyper->step.
+ * Only for 16 SH coefficients and 16-byte aligned arrays: EGS_E_UNSUPPORTED otherwise (use the two separate calls). */
+EGS_API int egm_backward_surfels_adam(const egs_frame* frame, int32_t first, int32_t count, const float* means3D,
+                                      float* shs, const float* scales, const float* rotations, const int32_t* radii,
+                                      const void* geom, const float* screen_grads, float* dL_dmeans3D,
+                                      float* dL_dopacity, float* dL_dscales, float* dL_drotations,
+                                      const egm_adam* hyper, float* m_shs, float* v_shs, void* stream);
+
 /* opacity = sigmoid(opacity_raw), scales = exp(scaling_raw), rotations = nan_to_num(normalize(rotation_raw), 1),
  * normals (may be NULL) = GaussianSurfels.get_normal. */
 EGS_API int egm_activate(int32_t P, const float* opacity_raw, const float* scaling_raw, const float* rotation_raw,

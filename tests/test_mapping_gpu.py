@@ -182,6 +182,23 @@ def test_autograd_level_equals_fused_mapper():
     losses_b = [n(fm.iterate(settings, frame, masks)).copy() for _ in range(2)]
     assert fm.ctx.read_counters()[2] == 0
     fm.synchronize()                       # no overflow: does not raise
+    # Adam on the SH block fused into the per-surfel backward (the default above, egm_backward_surfels_adam) against the
+    # two separate passes: the same update function on the same gradient.  Two runs differ by the order of the float
+    # atomics in the reverse walk (~1e-7), so the comparison is to that spread, not bit-wise.
+    assert fm.fuse_sh_adam
+    opt_c = M.FrameBatchOptimizer({k: t(v) for k, v in raw.items()}, lr, w)
+    fm_c = M.FusedMapper(opt_c, W, H, capacity=200000, sh_degree=deg, fuse_sh_adam=False)
+    losses_c = [n(fm_c.iterate(settings, frame, masks)).copy() for _ in range(2)]
+    for k in ("xyz", "shs", "opacity_raw", "scaling_raw", "rotation_raw"):
+        assert rel_err(n(getattr(opt_b, k)), n(getattr(opt_c, k))) <= 1e-6, k
+    # Adam's first steps move every coordinate by ~lr whatever the gradient's size, so a sign flip of a ~1e-12
+    # gradient (atomics order) moves exp_avg by its own magnitude: compare the state on its scale
+    for k in opt_b.state:
+        for j in (0, 1):
+            a, b = n(opt_b.state[k][j]), n(opt_c.state[k][j])
+            assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max() + 1e-30, (k, j)
+    assert np.allclose(np.stack(losses_b), np.stack(losses_c), rtol=1e-5)
+    assert float(opt_b.state["shs"][1].abs().max()) > 0
     # a mapper whose binning workspace is too small says so (at the next iterate / synchronize), instead of silently
     # optimising on truncated instance lists
     small = M.FusedMapper(M.FrameBatchOptimizer({k: t(v) for k, v in raw.items()}, lr, w), W, H, capacity=64,
