@@ -61,27 +61,13 @@ __device__ __forceinline__ void adam_sh_rows(const float* s_sh, const ShAdam& a,
 #define SH_BULK_PITCH 52   // floats per row for the bulk-copied layout: 208-B rows keep 16-B alignment and make the
                            // per-thread LDS.128 of a quarter-warp conflict-free (52 mod 32 = 20 -> 8 distinct 4-bank groups)
 
-// Sharded frames only: can this surfel reach one of the rank's tiles at all?  A cheap, conservative answer from the
-// projected centre and an upper bound of the splat radius -- lambda_max(cov2D) <= |J|_F^2 (mod max(sx, sy))^2 + 0.3, and
-// the reference's radius formula never exceeds 3 sqrt(2 lambda_max + 0.32) (its max(0.1, .) floor) -- so that the ~1500
-// instructions of the exact projection are spent only on the ~1/world of the surfels that can matter to this rank.
+// Sharded frames only: can this surfel reach one of the rank's tiles at all?  surfel_bound_rect (egs_surfel_math.cuh)
+// gives a conservative tile rectangle from the projected centre and an upper bound of the splat radius, so that the
+// ~1700 instructions of the exact projection are spent only on the ~1/world of the surfels that can matter here.
 __device__ __forceinline__ bool surfel_misses_mask(const FrameConst& fc, const float* mean, const float* scale,
-                                                   const uint32_t* __restrict__ mask_bits) {
-    const float px = mean[0], py = mean[1], pz = mean[2];
-    const float hw = xf_affine(fc.proj, 3, px, py, pz);
-    const float vz = xf_affine(fc.view, 2, px, py, pz);
-    if (!(vz > 0.05f) || !(hw > 0.05f)) return false;    // near / behind the camera: leave it to the exact path
-    const float pw = 1.0f / (hw + 0.0000001f);
-    const float ix = xf_affine(fc.proj, 0, px, py, pz) * pw * (float)fc.W * 0.5f + fc.cx;
-    const float iy = xf_affine(fc.proj, 1, px, py, pz) * pw * (float)fc.H * 0.5f + fc.cy;
-    const float smax = fc.mod * fmaxf(fabsf(scale[0]), fabsf(scale[1]));
-    const float lx = 1.3f * fc.tanfovx, ly = 1.3f * fc.tanfovy, iz = 1.0f / vz;
-    const float jf = (fc.fx * iz) * (fc.fx * iz) * (1.f + lx * lx) + (fc.fy * iz) * (fc.fy * iz) * (1.f + ly * ly);
-    const float lam = smax * smax * jf + 0.3f;
-    const float rad = ceilf(3.f * sqrtf(2.f * lam + 0.32f) * 1.001f) + 2.f;   // + 2 px: the centre above is not the exact one
-    if (!(rad < 16384.f)) return false;
+                                                   const float* rot, const uint32_t* __restrict__ mask_bits) {
     int x0, y0, x1, y1;
-    egs_tile_rect(ix, iy, (int)rad, fc.gx, fc.gy, x0, y0, x1, y1);
+    if (!surfel_bound_rect(fc, mean, scale, rot, x0, y0, x1, y1)) return false;   // undecided: leave it to the exact path
     const int w = x1 - x0, h = y1 - y0;
     if (w <= 0 || h <= 0) return true;                    // the bound rectangle is off the grid
     if (w * h > 48) return false;                         // a huge splat: not worth walking the mask
@@ -121,7 +107,7 @@ __host__ __device__ __forceinline__ int cand_region_cap(int P) {
 
 __global__ void __launch_bounds__(256)
 k_surfel_candidates(const egs_frame f, const float* __restrict__ means, const float* __restrict__ scales,
-                    const uint32_t* __restrict__ mask_bits, int own_first, int own_count, int32_t* __restrict__ radii,
+                    const float* __restrict__ rots, const uint32_t* __restrict__ mask_bits, int own_first, int own_count, int32_t* __restrict__ radii,
                     uint8_t* __restrict__ active, uint32_t* __restrict__ tiles_touched, int32_t* __restrict__ cand,
                     int32_t* __restrict__ cand_count) {
     __shared__ FrameConst fc;
@@ -135,7 +121,7 @@ k_surfel_candidates(const egs_frame f, const float* __restrict__ means, const fl
         bool keep = false;
         if (i < f.num_surfels) {
             keep = (i >= own_first && i - own_first < own_count) ||
-                   !surfel_misses_mask(fc, means + (size_t)3 * i, scales + (size_t)3 * i, mask_bits);
+                   !surfel_misses_mask(fc, means + (size_t)3 * i, scales + (size_t)3 * i, rots + (size_t)4 * i, mask_bits);
             if (!keep) {
                 radii[i] = 0;
                 active[i] = 0;
@@ -500,7 +486,7 @@ cudaError_t launch_surfel_forward(const egs_frame& f, const float* means, const 
             int32_t* cand_count = reinterpret_cast<int32_t*>(im.ticket);   // CAND_REGIONS words, zeroed by the plan's head memset
             const int groups = (P + 255) / 256;
             k_surfel_candidates<<<groups < 148 * 8 ? groups : 148 * 8, 256, 0, s>>>(
-                f, means, scales, im.mask_bits, own_first, own_count, radii, active, g.tiles_touched, g.cand, cand_count);
+                f, means, scales, rots, im.mask_bits, own_first, own_count, radii, active, g.tiles_touched, g.cand, cand_count);
             const int per_region = (cand_region_cap(P) + SURF_THREADS - 1) / SURF_THREADS;
             k_surfel_forward<3><<<CAND_REGIONS * per_region, 128, 0, s>>>(f, means, scales, rots, opac, shs, colors,
                                                                           tile_mask, g, im, radii, active, own_first,

@@ -53,6 +53,19 @@ void emu_surfel_forward(int P, int W, int H, int D, int M, float tanfovx, float 
     }
 }
 
+// the sharded projection's conservative footprint bound (surfel_bound_rect): rect[P][4], decided[P]
+void emu_surfel_bound_rect(int P, int W, int H, float tanfovx, float tanfovy, float cx, float cy, float mod,
+                           const float* view, const float* proj, const float* campos, const float* means,
+                           const float* scales, const float* rots, int32_t* rect, uint8_t* decided) {
+    const float bg[3] = {0.f, 0.f, 0.f};
+    const FrameConst fc = make_fc(W, H, 0, 1, tanfovx, tanfovy, cx, cy, mod, view, proj, campos, bg);
+    for (int i = 0; i < P; i++) {
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        decided[i] = surfel_bound_rect(fc, means + 3 * i, scales + 3 * i, rots + 4 * i, x0, y0, x1, y1) ? 1 : 0;
+        rect[4 * i] = x0; rect[4 * i + 1] = y0; rect[4 * i + 2] = x1; rect[4 * i + 3] = y1;
+    }
+}
+
 void emu_surfel_backward(int P, int W, int H, int D, int M, float tanfovx, float tanfovy, float cx, float cy, float mod,
                          const float* view, const float* proj, const float* campos, const float* bg, const float* means,
                          const float* scales, const float* rots, const float* shs, const int32_t* radii,

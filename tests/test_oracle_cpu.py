@@ -239,6 +239,49 @@ def _emu_forward(emu, cam, sc, deg, bg):
     return radii, act, rec, c3, cl, rect
 
 
+@pytest.mark.parametrize("variant", ["scene", "big_splats", "unnormalised_quaternions", "near_and_behind", "posed"])
+def test_footprint_bound_contains_the_exact_tile_rectangle(hostemu, variant):
+    """surfel_bound_rect (the sharded projection's pre-cull, egs_surfel_math.cuh) on the CPU: wherever it decides, its
+    tile rectangle contains the exact rectangle the product's surfel_forward computes -- so a surfel it rules out for a
+    rank can never have produced an instance there.  Also: it is not vacuous (it is much smaller than the grid)."""
+    from eggfusion_b200 import synthetic as syn
+    W, H, P = 640, 368, 20000
+    base = syn.default_camera(W, H)
+    cam = base if variant != "posed" else syn.default_camera(W, H, syn.look_from((0.3, -0.2, 0.25), 0.2, -0.15))
+    sc = syn.make_scene(P, base, layers=3, sh_degree=0)
+    rng = np.random.default_rng(11)
+    if variant == "big_splats":
+        sc["scales"][:, :2] *= rng.uniform(1.0, 40.0, size=(P, 1)).astype(np.float32)
+    if variant == "unnormalised_quaternions":
+        sc["rotations"] *= rng.uniform(0.3, 2.5, size=(P, 1)).astype(np.float32)
+    if variant == "near_and_behind":
+        sc["xyz"][:, 2] = rng.uniform(-0.3, 1.2, size=P).astype(np.float32)      # across the near plane and behind
+        sc["xyz"][:, :2] *= 0.4                                                    # so that many still land on screen
+    radii, act, rec, c3, cl, rect = _emu_forward(hostemu, cam, sc, 0, np.zeros(3, np.float32))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    F = C.c_float
+    brect = np.zeros((P, 4), np.int32)
+    decided = np.zeros(P, np.uint8)
+    view, proj, cp = cam.viewmatrix.reshape(-1).copy(), cam.projmatrix.reshape(-1).copy(), cam.campos.copy()
+    hostemu.emu_surfel_bound_rect(P, W, H, F(cam.tanfovx), F(cam.tanfovy), F(cam.cx), F(cam.cy), F(1.0), p(view), p(proj),
+                                  p(cp), p(sc["xyz"]), p(sc["scales"]), p(sc["rotations"]), p(brect), p(decided))
+    vis = radii > 0
+    area = (rect[:, 2] - rect[:, 0]) * (rect[:, 3] - rect[:, 1])
+    check = vis & (area > 0) & (decided != 0)
+    assert int(check.sum()) > (100 if variant == "near_and_behind" else 1000)
+    e, b_ = rect[check], brect[check]
+    inside = (b_[:, 0] <= e[:, 0]) & (b_[:, 1] <= e[:, 1]) & (b_[:, 2] >= e[:, 2]) & (b_[:, 3] >= e[:, 3])
+    assert bool(inside.all()), (variant, int((~inside).sum()), e[~inside][:3], b_[~inside][:3])
+    # every visible surfel with a non-empty rectangle the bound does NOT decide is kept by the caller: nothing to check;
+    # but the bound must decide almost all of them and must not be the whole grid
+    assert float((decided[vis & (area > 0)] != 0).mean()) > 0.95
+    if variant in ("scene", "posed"):
+        barea = (b_[:, 2] - b_[:, 0]) * (b_[:, 3] - b_[:, 1])
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        assert float(np.median(barea)) <= 4.0 * float(np.median(area[check])) + 4.0
+        assert float(barea.mean()) < 0.1 * gx * gy
+
+
 @pytest.mark.parametrize("name", ["c1_posed_bg", "small_deg0_ragged", "small_deg2"])
 def test_product_surfel_math_on_host_matches_oracle(hostemu, name):
     """egs_surfel_math.cuh compiled for the CPU: bit-exact index-critical quantities, tight tolerance elsewhere."""
