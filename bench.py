@@ -499,6 +499,97 @@ def reference_ingest_factory(dev, color, depth_raw, mask, intr):
     return ingest
 
 
+def _stock_reference_paths():
+    """sys.path for importing the reference's own python (`src.*` from oracle/_ref/egg, a byte copy of /root/reference/src
+    made by oracle/build_ref.sh) on its own native builds; False where that copy did not travel."""
+    egg = os.path.join(ROOT, "oracle", "_ref", "egg")
+    if not os.path.isdir(os.path.join(egg, "src")):
+        return False
+    for p_ in (os.path.join(ROOT, "tests", "shims"), os.path.join(ROOT, "oracle", "_ref"),
+               os.path.join(ROOT, "tests", "shims_ref"), egg):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    return True
+
+
+def stock_mapping_iteration_factory(raw, frames, cams, deg):
+    """One iteration of Mapper.frame_batch_optimization driven through the reference's OWN code:
+    `GaussianSurfels` (parametrize -> torch.optim.Adam, the get_* activations), `Mapping.total_params`,
+    `Renderer.render` (its own rasterizer build) and `Mapping.compute_loss` are the stock classes / methods of
+    oracle/_ref/egg/src/core; only the loop body around them (mapper.py:349-365: render, loss, backward, step,
+    zero_grad, loss.item()) is written out here, on a Mapping instance that carries just the attributes those methods
+    read.  Returns None where the copy of the reference's python is absent."""
+    import math
+    import types
+    import torch
+    if not _stock_reference_paths():
+        return None
+    from easydict import EasyDict as edict
+    from src.core.gaussian_surfels import GaussianSurfels
+    from src.core.mapper import Mapping
+    from src.core.render import Renderer
+    cfg = edict({"Surfel": {"init_opacity": 0.99, "scale_factor": 1.0, "min_radius": 0.0, "max_radius": 1.0,
+                            "max_sh_degree": deg, "active_sh_degree": deg, "stable_grad_coeff": 1.0,
+                            "confidence_thres": 10.0}})
+    surf = GaussianSurfels(cfg)
+    surf._xyz, surf._features_dc, surf._features_rest = raw["xyz"].clone(), raw["features_dc"].clone(), raw["features_rest"].clone()
+    surf._scaling, surf._rotation, surf._opacity = raw["scaling"].clone(), raw["rotation"].clone(), raw["opacity"].clone()
+    m = object.__new__(Mapping)
+    m.surfels0 = surf
+    m.renderer = Renderer(cfg)
+    for k, v in MAP_WEIGHTS.items():
+        setattr(m, k, v)
+    opt = torch.optim.Adam(surf.parametrize(edict(MAP_LR)), lr=0.0)
+    geo = {"position": surf.get_xyz.detach(), "normal": surf.get_normal.detach()}      # mapper.py:342-345
+    dev = raw["xyz"].device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    views = [types.SimpleNamespace(fovx=2.0 * math.atan(c.tanfovx), fovy=2.0 * math.atan(c.tanfovy), height=c.height,
+                                   width=c.width, cx=c.cx, cy=c.cy, full_proj_transform=t(c.projmatrix),
+                                   world_view_transform=t(c.viewmatrix), camera_center=t(c.campos)) for c in cams]
+    losses = []
+
+    def iteration(i):
+        ci = i % len(frames)
+        fmap, (rgb_mask, geo_mask) = frames[ci]
+        out = m.renderer.render(views[ci], m.total_params)
+        loss = m.compute_loss(out, fmap, (rgb_mask, geo_mask), geo)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(loss.item())
+    return iteration, losses
+
+
+def stock_tracking_frame_factory(model, frame, T0):
+    """The dense part of Tracker.tracking_frame through the reference's OWN `Tracker.tracking_optimization`
+    (tracker.py:194-251: projective_transform, icp_optimization, rgb_optimization, solve_block, the .item() convergence
+    test) and `update_transform` (optimizer.py:426-441); the two nested loops of tracker.py:153-164 are written out
+    around them.  `solve_block` is the reference's binding with its CPU Eigen solve replaced by torch.linalg.lstsq on the
+    CPU (tests/shims_ref: Eigen is absent).  Returns None where the reference's python did not travel."""
+    if not _stock_reference_paths():
+        return None
+    from src.core.optimizer import update_transform
+    from src.core.tracker import Tracker
+    cfg = TRACK_CFG
+    tr = object.__new__(Tracker)
+    tr.pyramid_level, tr.pyramid_iters = cfg["pyramid_level"], list(cfg["pyramid_iters"])
+    tr.angle_thres, tr.dist_thres = cfg["angle_threshold"], cfg["distance_threshold"]
+    tr.residual_thres, tr.dx_thres = cfg["residual_thres"], cfg["dx_threshold"]
+    tr.use_rgb, tr.rgb_weight, tr.use_sparse = cfg["use_rgb"], cfg["rgb_weight"], False
+
+    def track(_i):
+        dense = T0.clone()
+        conv_any = False
+        for l in range(tr.pyramid_level):
+            for _ in range(tr.pyramid_iters[l]):
+                level = tr.pyramid_level - 1 - l
+                dx, converged = tr.tracking_optimization(model, frame, level, dense, 0)
+                dense = update_transform(dense, dx)
+                conv_any = conv_any or converged
+        return dense, conv_any
+    return track
+
+
 # ------------------------------------------------------------------------------------------------ the reference's own loop
 def slam_loop(arm, frames=24):
     """BASELINE configs 2 and 5: frames/s of the reference's UNMODIFIED Python loop (oracle/_ref/egg, byte copy of
@@ -1202,16 +1293,44 @@ def run_reference(args):
     mapping = None
     if not args.no_mapping:
         raw, frames = mapping_inputs(scene, cams, dev)
-        it, mlosses = reference_mapping_iteration_factory(ref, raw, frames, settings, deg)
+        stock = None
+        try:
+            stock = stock_mapping_iteration_factory(raw, frames, cams, deg)
+            if stock is not None:
+                stock[0](0)                      # one iteration up front: any import / attribute problem shows here
+        except Exception as ex:
+            print("bench: the stock reference mapping iteration is unavailable (%r); timing the restated flow" % (ex,),
+                  file=sys.stderr)
+            stock = None
+        if stock is not None:
+            it, mlosses = stock
+            how = ("the reference's own code: GaussianSurfels + Mapping.total_params + Renderer.render (its rasterizer "
+                   "build) + Mapping.compute_loss from oracle/_ref/egg/src/core, torch.optim.Adam over "
+                   "GaussianSurfels.parametrize, loss.item()")
+        else:
+            it, mlosses = reference_mapping_iteration_factory(ref, raw, frames, settings, deg)
+            how = ("the reference rasterizer and the reference's torch glue restated (activations, compute_loss incl. "
+                   "check_nan, backward, torch Adam, loss.item())")
         ms_map = time_loop(it, max(3, args.warmup), args.steps)
         mapping = {"ms_per_iter": ms_map, "iters_per_s": 1e3 / ms_map, "last_loss": mlosses[-1],
-                   "what": "one Mapper.frame_batch_optimization iteration with the reference rasterizer and the "
-                           "reference's torch glue (activations, compute_loss incl. check_nan, backward, torch Adam, "
-                           "loss.item())"}
+                   "what": "one Mapper.frame_batch_optimization iteration: " + how}
     tracking = None
     if not args.no_tracking:
         pm, pf, T0 = tracking_inputs(dev)
-        track = reference_tracking_frame_factory(pm, pf, T0)
+        track, how_t = None, ""
+        try:
+            track = stock_tracking_frame_factory(pm, pf, T0)
+            if track is not None:
+                track(0)
+                how_t = ("the reference's own Tracker.tracking_optimization + update_transform (oracle/_ref/egg/src/core; "
+                         "solve_block: its binding with the CPU Eigen solve replaced by torch.linalg.lstsq on the CPU)")
+        except Exception as ex:
+            print("bench: the stock reference tracker is unavailable (%r); timing the restated flow" % (ex,), file=sys.stderr)
+            track = None
+        if track is None:
+            track = reference_tracking_frame_factory(pm, pf, T0)
+            how_t = ("the reference's PyTorch flow restated (projective_transform, icp_optimization, rgb_optimization, "
+                     "CPU solve, .item() convergence test)")
         last = {}
 
         def trk_frame(i):
@@ -1219,8 +1338,7 @@ def run_reference(args):
         ms_trk = time_loop(trk_frame, max(3, args.warmup), max(5, args.steps // 5))
         tracking = {"ms_per_frame": ms_trk, "frames_per_s": 1e3 / ms_trk, "converged": bool(last["conv"]),
                     "dense_delta_t": [float(v) for v in last["T"][:3, 3]],
-                    "what": "dense part of Tracker.tracking_frame with the reference's PyTorch flow (projective_transform, "
-                            "icp_optimization, rgb_optimization, CPU solve, .item() convergence test)"}
+                    "what": "dense part of Tracker.tracking_frame (9 Gauss-Newton steps, 3 levels): " + how_t}
     ingest = None
     if not args.no_tracking:
         ic, idp, im_, iintr = ingest_inputs(dev)
