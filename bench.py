@@ -1175,7 +1175,7 @@ def run_ours(args):
     if world == 1 and not args.no_loop:
         torch.cuda.empty_cache()
         line["slam_loop"] = slam_loop("ours")
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -1198,13 +1198,13 @@ def run_reference(args):
     if not have_gpu_ref:
         # no compiled reference on this box: time the CPU port of its algorithm on a bounded sample
         cb = cpu_baseline_sample(scene, cams, grads, deg)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+        emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
                           "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": config_dict(args.workload, P, W, H, deg, M, cb.get("instances_per_frame", 0.0)),
                           "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
-                                  "d2h_bytes_per_step": 0}}))
+                                  "d2h_bytes_per_step": 0}})
         return
     import torch
     ref = ref_loader.load()
@@ -1369,7 +1369,26 @@ def run_reference(args):
     if not args.no_loop:
         torch.cuda.empty_cache()
         line["slam_loop"] = slam_loop("reference")
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on the
+    first communicator, the reference's loop prints progress): from here on file descriptor 1 points at stderr and the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
 
 
 def main():
@@ -1391,6 +1410,7 @@ def main():
     ap.add_argument("--no-loop", action="store_true", help="skip the reference-loop frames/s (configs 2 and 5)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
