@@ -47,6 +47,47 @@ def test_workspace_sizes_no_gpu_needed():
     assert g0 > 0 and i0 > 0 and b0 > 0
 
 
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Argument checks of the sharded / fused entry points return EGS_E_BADARG / EGS_E_UNSUPPORTED before any CUDA
+    call is made (so they can be exercised without a GPU): the error behaviour a binding in another language relies on."""
+    import ctypes as C
+    from eggfusion_b200 import _lib
+    lib = _lib.load()
+    BAD, UNSUP = -1, -2
+    dummy = C.create_string_buffer(256)
+    ptr = C.addressof(dummy)                              # a non-null pointer that is never dereferenced
+    good = _lib.Frame(1000, 64, 64, 3, 16, 1.0, 1.0, 32.0, 32.0, 1.0, ptr, ptr, ptr, ptr)
+    nocam = _lib.Frame(1000, 64, 64, 3, 16, 1.0, 1.0, 32.0, 32.0, 1.0, None, ptr, ptr, ptr)
+    deg9 = _lib.Frame(1000, 64, 64, 9, 16, 1.0, 1.0, 32.0, 32.0, 1.0, ptr, ptr, ptr, ptr)
+    sh4 = _lib.Frame(1000, 64, 64, 1, 4, 1.0, 1.0, 32.0, 32.0, 1.0, ptr, ptr, ptr, ptr)
+    # sharded plan: null frame, frame without camera tensors, unsupported degree, owned range outside [0, P]
+    args = [ptr] * 6 + [None]
+    assert lib.egs_forward_plan_sharded(None, *args, 0, 10, ptr, ptr, ptr, ptr, None, None) == BAD
+    assert lib.egs_forward_plan_sharded(C.byref(nocam), *args, 0, 10, ptr, ptr, ptr, ptr, None, None) == BAD
+    assert lib.egs_forward_plan_sharded(C.byref(deg9), *args, 0, 10, ptr, ptr, ptr, ptr, None, None) == UNSUP
+    assert lib.egs_forward_plan_sharded(C.byref(good), *args, 0, 10, ptr, None, ptr, ptr, None, None) == BAD   # img workspace
+    # exchange: the chunk must be a positive multiple of 256 rows, the rank inside the world, the tables present
+    assert lib.egs_push_rows(1000, 100, 2, 0, ptr, ptr, ptr, ptr, ptr, None) == BAD
+    assert lib.egs_push_rows(1000, 512, 2, 2, ptr, ptr, ptr, ptr, ptr, None) == BAD
+    assert lib.egs_push_rows(1000, 512, 2, 0, ptr, ptr, None, ptr, ptr, None) == BAD
+    assert lib.egs_push_rows(1000, 512, 2, 0, None, ptr, ptr, ptr, ptr, None) == BAD
+    assert lib.egs_fold_inbox(0, 2, 0, ptr, ptr, ptr, None) == BAD
+    assert lib.egs_fold_inbox(512, 2, 0, None, ptr, ptr, None) == BAD
+    # fused backward + SH Adam: hyper-parameters required, step >= 1, only the 16-coefficient layout
+    h = _lib.AdamHyper()
+    h.beta1, h.beta2, h.eps, h.step = 0.9, 0.999, 1e-8, 1
+    sig = [ptr] * 11
+    assert lib.egm_backward_surfels_adam(C.byref(good), 0, 10, *sig, None, ptr, ptr, None) == BAD
+    h0 = _lib.AdamHyper()
+    assert lib.egm_backward_surfels_adam(C.byref(good), 0, 10, *sig, C.byref(h0), ptr, ptr, None) == BAD      # step 0
+    assert lib.egm_backward_surfels_adam(C.byref(good), 990, 20, *sig, C.byref(h), ptr, ptr, None) == BAD     # range
+    assert lib.egm_backward_surfels_adam(C.byref(good), 0, 10, *sig, C.byref(h), None, ptr, None) == BAD      # no state
+    assert lib.egm_backward_surfels_adam(C.byref(sh4), 0, 10, *sig, C.byref(h), ptr, ptr, None) == UNSUP
+    assert lib.egm_backward_surfels_adam(C.byref(good), 0, 10, *sig, C.byref(h), ptr + 4, ptr, None) == UNSUP  # alignment
+    assert lib.egm_backward_surfels_adam(C.byref(good), 0, 0, *sig, C.byref(h), ptr, ptr, None) == 0           # empty range
+    assert b"unsupported" in lib.egs_error_string(UNSUP)
+
+
 def test_sm100a_sass_present():
     so = os.path.join(ROOT, "eggfusion_b200", "libeggsplat.so")
     out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
