@@ -3,17 +3,20 @@
 The reference is single-GPU; its `tile_mask` argument (forward.cu:292-300, rasterizer_impl.cu:103-111) is the seam:
 a surfel only emits instances for tiles whose mask is non-zero.  Scheme:
 
-  * every rank holds the full (activated) surfel parameter set; the per-surfel projection runs for all of it, but the
-    colour (SH) evaluation and the record / backward state are produced only for surfels that touch one of the rank's
-    tiles or lie in its owned surfel range (`egs_forward_plan_sharded`);
-  * rank r bins / sorts / composites only its tile set (interleaved tile rows, or cost-balanced from the previous
-    frame's per-tile list lengths) and runs the reverse walk over the same tiles -> partial rows of the screen-gradient
-    block G[P][16] for the ~P/world surfels it touched;
-  * ONE exchange: every rank adds the rows it touched to their owners' accumulation blocks in NVLink peer memory
-    (`egs_push_rows`: 16-byte `red.global.add` on peer-mapped addresses, performed by the owner's L2; symmetric memory
-    from torch.distributed._symmetric_memory) and a device-side barrier follows.  Only touched rows cross the links
-    (C3 at 8 GPUs: ~14 MB per rank instead of the 56 MB of a dense reduce-scatter).  Without peer memory (gloo, no
-    P2P) the same sum is one `reduce_scatter_tensor` over NCCL;
+  * every rank holds the full (activated) surfel parameter set.  The exact per-surfel projection, the colour (SH)
+    evaluation and the record / backward state are produced only for surfels that can reach one of the rank's tiles or
+    lie in its owned surfel range (`egs_forward_plan_sharded`: from 3 ranks on a cheap conservative footprint bound
+    first compacts those candidates, the projection then runs on them alone);
+  * rank r bins / sorts / composites only its tile set -- a contiguous run of the row-major tile sequence with 1/world
+    of the summed cost (per-tile list lengths of previous frames; `tile_partition`), or interleaved tile rows when no
+    costs are known -- and runs the reverse walk over the same tiles -> partial rows of the screen-gradient block
+    G[P][16] for the ~P/world surfels it touched;
+  * ONE exchange (`PeerExchange`): the rows a rank touched are compacted per 256-surfel group and stored into its
+    section of their owners' inboxes in NVLink peer memory (`egs_push_rows`: one TMA bulk store per group on the
+    peer-mapped address; symmetric memory from torch.distributed._symmetric_memory), a device-side barrier follows, and
+    every owner folds its inbox sections into its block (`egs_fold_inbox`).  Only touched rows cross the links (C3 at 8
+    GPUs: ~12 MB per rank instead of the 56 MB of a dense reduce-scatter).  Without peer memory (gloo, no P2P) the
+    same sum is one `reduce_scatter_tensor` over NCCL;
   * rank r runs the per-surfel backward for its surfel range -> gradient shards [first, first + count);
   * a distributed optimiser step (`DistributedMapper`): Adam on the owned range, then `all_gather_into_tensor` of the
     updated activated parameters.
