@@ -127,8 +127,9 @@ EGS_API int egs_forward_plan_sharded(const egs_frame* frame, const float* means3
 /*
  * Exchange step of a tile-sharded frame over peer memory (one process per GPU, NVLink / NVSwitch), sender side: moves
  * the rows of `local_screen_grads` [P][16] that this rank's reverse walk touched into this sender's section of their
- * owners' inboxes (compacted per 256-surfel group, streamed with coalesced stores on peer-mapped addresses; the surfel
- * id travels in the row's last padding word), clears them locally and publishes the per-owner row counts.
+ * owners' inboxes (compacted per 256-surfel group in shared memory and sent with one bulk store -- cp.async.bulk,
+ * the TMA engine -- on the peer-mapped address; the surfel id travels in the row's last padding word), clears them
+ * locally and publishes the per-owner row counts.
  * Owner r owns surfels [r * chunk_rows, (r+1) * chunk_rows); chunk_rows must be a multiple of 256.
  * peer_inboxes / peer_headers: DEVICE arrays of `world` pointers to rank r's inbox (float [world][chunk_rows][16]) and
  * header (int32 [world]) as THIS process maps them.  sent_counters: device uint32 [world], zero before the first call
