@@ -656,7 +656,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        with _stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()                      # the communicator (and NCCL's banner) happen here at the latest
+            torch.cuda.synchronize(dev)
     E.load()
     empty = torch.Tensor([])
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -1372,23 +1375,27 @@ def run_reference(args):
     emit(line)
 
 
-_JSON_OUT = None
+import contextlib
 
 
-def _claim_stdout():
-    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on the
-    first communicator, the reference's loop prints progress): from here on file descriptor 1 points at stderr and the
-    JSON line goes to a private duplicate of the original stdout."""
-    global _JSON_OUT
-    if _JSON_OUT is None:
+@contextlib.contextmanager
+def _stdout_to_stderr():
+    """The contract is ONE JSON line on stdout, and NCCL prints its version banner there when the first communicator
+    is created: file descriptor 1 points at stderr for the duration of the block (nothing else is moved -- whatever the
+    harness itself writes to stdout before or after stays where it was)."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
         sys.stdout.flush()
-        _JSON_OUT = os.fdopen(os.dup(1), "w")
-        os.dup2(2, 1)
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 def emit(line):
-    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
-    print(json.dumps(line), file=out, flush=True)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -1410,7 +1417,6 @@ def main():
     ap.add_argument("--no-loop", action="store_true", help="skip the reference-loop frames/s (configs 2 and 5)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
-    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

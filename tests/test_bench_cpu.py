@@ -45,3 +45,19 @@ def test_workload_shapes():
     P = scene["xyz"].shape[0]
     assert P == 10_000 and deg == 3 and scene["shs"].shape == (P, 16, 3) and len(cams) == 4 == len(grads)
     assert cams[0].width == 256 and grads[0]["color"].shape == (3, 256, 256)
+
+
+def test_stdout_guard_moves_only_what_is_written_inside_it():
+    """bench._stdout_to_stderr (wrapped around NCCL's communicator creation, whose version banner goes to stdout): bytes
+    written to file descriptor 1 inside the block land on stderr, everything before and after stays on stdout."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "print('before', flush=True)\n"
+            "with bench._stdout_to_stderr():\n"
+            "    os.write(1, b'NCCL version banner\\n')\n"
+            "bench.emit({'metric': 'x'})\n"
+            "os.write(1, b'after\\n')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
+    assert r.stdout.splitlines() == ["before", '{"metric": "x"}', "after"]
+    assert "NCCL version banner" in r.stderr
